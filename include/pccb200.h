@@ -1,0 +1,91 @@
+/*
+ * pccb200.h — C ABI of libpccb200.so: B200 (sm_100a) implementation of the V-PCC (TMC2 v24.0) encoder-side
+ * patch-generation + packing + image-formation hot path and of PCCCodec::generatePointCloud.
+ *
+ * The reference has no FFI today (it is one C++ process); these are the entry points a maintainer binds from
+ * PccLibEncoder / PccLibCommon in place of the CPU bodies.  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference checkout, source/lib/...).  INTEGRATION.md shows the C++ shim.
+ *
+ * Conventions: plain pointers + sizes, host buffers owned by the caller, device memory owned by the library.
+ * Every function returns 0 on success or a negative pccb200_status; nothing calls exit().  The library needs
+ * a CUDA device: there is no CPU fallback (pccb200_create fails with PCCB200_ERR_NO_DEVICE).
+ */
+#ifndef PCCB200_H
+#define PCCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pccb200_status {
+  PCCB200_OK              = 0,
+  PCCB200_ERR_NO_DEVICE   = -1, /* no CUDA device / driver: the product has no CPU path                 */
+  PCCB200_ERR_CUDA        = -2, /* a CUDA call failed; see pccb200_last_error                           */
+  PCCB200_ERR_BAD_ARG     = -3,
+  PCCB200_ERR_STATE       = -4, /* stage called out of order                                            */
+  PCCB200_ERR_CAPACITY    = -5, /* caller buffer too small                                              */
+  PCCB200_ERR_UNSUPPORTED = -6, /* parameter combination outside the implemented (CTC) hot path         */
+  PCCB200_ERR_CANVAS      = -180 /* patch2Canvas out of bounds (reference: exit(180), PCCPatch.cpp:238) */
+} pccb200_status;
+
+/* Parameters of PCCPatchSegmenter3Parameters that the CTC hot path reads
+ * (PccLibEncoder/include/PCCPatchSegmenter.h:48-99, filled by PCCEncoder::generateSegments,
+ *  PccLibEncoder/source/PCCEncoder.cpp:4672-4727). Defaults in comments = CTC all-intra r3 longdress. */
+typedef struct pccb200_seg_params {
+  int32_t nn_normal_estimation;            /* 16  */
+  int32_t normal_orientation;              /* 1 = spanning tree (0 none) */
+  int32_t max_nn_count_refine;             /* 1024 */
+  int32_t iteration_count_refine;          /* 50 (longdress), 10 common */
+  int32_t voxel_dim_refine;                /* 4   */
+  int32_t search_radius_refine;            /* 192 */
+  int32_t occupancy_resolution;            /* 16  */
+  int32_t enable_patch_splitting;          /* 1   */
+  int32_t max_patch_size;                  /* 1024 */
+  int32_t quantizer_size_x;                /* 16 = 1<<log2QuantizerSizeX */
+  int32_t quantizer_size_y;                /* 16  */
+  int32_t min_point_count_per_cc;          /* 16  */
+  int32_t max_nn_count_patch_seg;          /* 16  */
+  int32_t surface_thickness;               /* 4   */
+  int32_t min_level;                       /* 64  */
+  int32_t max_allowed_depth;               /* 255 = (1<<geometryNominal2dBitdepth)-1 */
+  int32_t geometry_bitdepth_2d;            /* 8   */
+  int32_t geometry_bitdepth_3d;            /* 11 = geometry3dCoordinatesBitdepth+1 */
+  int32_t map_count_minus1;                /* 1   */
+  int32_t reserved0;
+  double  lambda_refine;                   /* 3.0 */
+  double  max_allowed_dist2_raw_detection; /* 9.0 */
+  double  max_allowed_dist2_raw_selection; /* 1.0 */
+  double  weight_normal[3];                /* PCCEncoder::calculateWeightNormal (frame 0 of the GOF) */
+} pccb200_seg_params;
+
+/* One patch: the fields of PCCPatch (PccLibCommon/include/PCCPatch.h:353-409) that the hot path produces
+ * and that downstream reference code (packing, createPatchFrameDataStructure, generatePointCloud) reads. */
+typedef struct pccb200_patch {
+  int32_t index;          /* creation order == PCCPatch::index_ */
+  int32_t view_id;        /* 0..5, PCCPatch::setViewId (PCCPatch.cpp:111-138) */
+  int32_t normal_axis, tangent_axis, bitangent_axis, projection_mode;
+  int32_t u1, v1, d1;     /* 3-D offsets */
+  int32_t size_u, size_v; /* depth-map size in pixels */
+  int32_t size_d, size_d_pixel;
+  int32_t size_u0, size_v0;   /* size in occupancy blocks */
+  int32_t size_2d_x, size_2d_y; /* patchSize2D{X,Y}InPixel (quantised) */
+  int32_t u0, v0, orientation;  /* filled by packing; -1 before */
+  int32_t d0_count, eom_and_d1_count;
+  int64_t depth_offset;   /* into the int16 depth arena: depth_[0] then depth_[1], size_u*size_v each */
+  int64_t occ_offset;     /* into the uint8 occupancy arena: size_u0*size_v0 */
+} pccb200_patch;
+
+typedef struct pccb200_ctx pccb200_ctx;
+
+/* library / device lifetime */
+int         pccb200_create( int device, pccb200_ctx** out );
+void        pccb200_destroy( pccb200_ctx* ctx );
+const char* pccb200_last_error( const pccb200_ctx* ctx );
+const char* pccb200_version( void );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCCB200_H */

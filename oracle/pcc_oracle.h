@@ -1,0 +1,67 @@
+/*
+ * pcc_oracle.h — C ABI of the CPU *oracle* for the V-PCC patch-generation / image-formation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a from-scratch, single-threaded CPU restatement of the reference
+ * algorithms (MPEGGroup/mpeg-pcc-tmc2 v24.0); each function cites the reference file:line it restates.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load it.
+ * The product (mpeg-pcc-tmc2_b200/csrc, libpccb200.so) never links, imports or calls anything here.
+ *
+ * Parity status: PINNED — every entry point is checked against the reference itself compiled from
+ * /root/reference (oracle/_ref/libtmc2ref.so, see oracle/Makefile + oracle/ref_harness.cpp) in
+ * tests/test_oracle_vs_ref.py, and against committed fixtures in tests/golden/ generated from that build.
+ */
+#ifndef PCC_ORACLE_H
+#define PCC_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#include "../include/pccb200.h" /* shared POD parameter / patch structs (layout contract only) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- a1: nanoflann-equivalent kd-tree (PCCKdTree.cpp:42-79, nanoflann.hpp:1041-1254) ---------------- */
+void*  pcco_kdtree_build( const int16_t* xyz, size_t n );
+void   pcco_kdtree_free( void* tree );
+/* permutation of point indices in tree (leaf) order == nanoflann's vind after buildIndex */
+void   pcco_kdtree_vind( void* tree, uint32_t* vind );
+/* k-NN of nq queries; idx/dist2 are row-major nq x k, rows padded with 0xFFFFFFFF / -1 when the tree holds
+ * fewer than k points. Order inside a row == nanoflann KNNResultSet order (distance, then first-visited). */
+void   pcco_knn( void* tree, const int16_t* q, size_t nq, int k, uint32_t* idx, float* dist2 );
+/* radius search (dist2 < radius2), results sorted by (dist2, index) as nanoflann's IndexDist_Sorter does,
+ * truncated to max_results per query (PCCKdTree.cpp:65-79). CSR output; returns total entries written.
+ * Call with idx==NULL to size. offsets has nq+1 entries. */
+size_t pcco_radius( void* tree, const int16_t* q, size_t nq, double radius2, size_t max_results, uint64_t* offsets,
+                    uint32_t* idx, float* dist2 );
+
+/* ---- a2/a3: normals (PCCNormalsGenerator.cpp:71-185) and orientation (:198-242, :521-548) ---------- */
+/* nbr: n x k neighbour lists from pcco_knn on the same cloud. normals: n x 3 doubles.
+ * orientation: 0 none, 1 spanning tree. */
+void pcco_normals( const int16_t* xyz, size_t n, const uint32_t* nbr, int k, double* normals );
+void pcco_orient_normals( const int16_t* xyz, size_t n, const uint32_t* nbr, int k, double* normals );
+
+/* ---- a4: axis weights (PCCEncoder.cpp:3569-3626) ----------------------------------------------------- */
+void pcco_weight_normal( const int16_t* xyz, size_t n, int geometry_bitdepth_3d, double min_weight_epp, double w[3] );
+
+/* ---- a5/a6: initial + grid-based refined segmentation (PCCPatchSegmenter.cpp:226-265, 1386-1561) ----- */
+void pcco_initial_segmentation( const double* normals, size_t n, const double w[3], uint8_t* partition );
+void pcco_refine_segmentation( const int16_t* xyz, const double* normals, size_t n, const pccb200_seg_params* p,
+                               uint8_t* partition );
+
+/* ---- a7–a11: patch segmentation (PCCPatchSegmenter.cpp:537-1320) ------------------------------------ */
+/* Returns an opaque patch list; query with the accessors below. */
+void*  pcco_segment_patches( const int16_t* xyz, const uint8_t* rgb, size_t n, const uint32_t* nbr, int k,
+                             const uint8_t* partition, const pccb200_seg_params* p );
+int    pcco_patches_count( void* pl );
+size_t pcco_patches_depth_elems( void* pl );
+size_t pcco_patches_occ_elems( void* pl );
+void   pcco_patches_get( void* pl, pccb200_patch* patches, int16_t* depth_arena, uint8_t* occ_arena );
+void   pcco_patches_free( void* pl );
+
+/* ---- whole-frame convenience: a1..a11 (PCCPatchSegmenter3::compute, PCCPatchSegmenter.cpp:53-150) ---- */
+void* pcco_segment_frame( const int16_t* xyz, const uint8_t* rgb, size_t n, const pccb200_seg_params* p );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,276 @@
+"""ctypes bindings used by the tests: the CPU oracle (oracle/libpccoracle.so), the compiled reference
+(oracle/_ref/libtmc2ref.so, optional: present only where it was built) and the product (libpccb200.so).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "libpccoracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libtmc2ref.so")
+PRODUCT_SO = os.path.join(ROOT, "mpeg-pcc-tmc2_b200", "libpccb200.so")
+
+c_i16p = C.POINTER(C.c_int16)
+c_u8p = C.POINTER(C.c_uint8)
+c_u32p = C.POINTER(C.c_uint32)
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+c_u64p = C.POINTER(C.c_uint64)
+
+
+class SegParams(C.Structure):
+    """mirror of pccb200_seg_params (include/pccb200.h)"""
+    _fields_ = [(n, C.c_int32) for n in (
+        "nn_normal_estimation", "normal_orientation", "max_nn_count_refine", "iteration_count_refine",
+        "voxel_dim_refine", "search_radius_refine", "occupancy_resolution", "enable_patch_splitting",
+        "max_patch_size", "quantizer_size_x", "quantizer_size_y", "min_point_count_per_cc",
+        "max_nn_count_patch_seg", "surface_thickness", "min_level", "max_allowed_depth",
+        "geometry_bitdepth_2d", "geometry_bitdepth_3d", "map_count_minus1", "reserved0")] + [
+        ("lambda_refine", C.c_double), ("max_allowed_dist2_raw_detection", C.c_double),
+        ("max_allowed_dist2_raw_selection", C.c_double), ("weight_normal", C.c_double * 3)]
+
+
+def ctc_seg_params(bits=10, iterations=50, weight=(1.0, 1.0, 1.0)):
+    """CTC all-intra values."""
+    p = SegParams()
+    p.nn_normal_estimation = 16
+    p.normal_orientation = 1
+    p.max_nn_count_refine = 1024
+    p.iteration_count_refine = iterations
+    p.voxel_dim_refine = 4
+    p.search_radius_refine = 192
+    p.occupancy_resolution = 16
+    p.enable_patch_splitting = 1
+    p.max_patch_size = 1024
+    p.quantizer_size_x = 16
+    p.quantizer_size_y = 16
+    p.min_point_count_per_cc = 16
+    p.max_nn_count_patch_seg = 16
+    p.surface_thickness = 4
+    p.min_level = 64
+    p.max_allowed_depth = 255
+    p.geometry_bitdepth_2d = 8
+    p.geometry_bitdepth_3d = bits + 1
+    p.map_count_minus1 = 1
+    p.lambda_refine = 3.0
+    p.max_allowed_dist2_raw_detection = 9.0
+    p.max_allowed_dist2_raw_selection = 1.0
+    for i in range(3):
+        p.weight_normal[i] = weight[i]
+    return p
+
+
+class Patch(C.Structure):
+    """mirror of pccb200_patch"""
+    _fields_ = [(n, C.c_int32) for n in (
+        "index", "view_id", "normal_axis", "tangent_axis", "bitangent_axis", "projection_mode",
+        "u1", "v1", "d1", "size_u", "size_v", "size_d", "size_d_pixel", "size_u0", "size_v0",
+        "size_2d_x", "size_2d_y", "u0", "v0", "orientation", "d0_count", "eom_and_d1_count")] + [
+        ("depth_offset", C.c_int64), ("occ_offset", C.c_int64)]
+
+
+PATCH_DTYPE = np.dtype([(n, np.int32) for n, _ in Patch._fields_[:22]] + [("depth_offset", np.int64), ("occ_offset", np.int64)])
+assert PATCH_DTYPE.itemsize == C.sizeof(Patch)
+
+
+def ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _xyz(a):
+    a = np.ascontiguousarray(a, dtype=np.int16)
+    assert a.ndim == 2 and a.shape[1] == 3
+    return a
+
+
+class PatchSet:
+    """patch metadata (structured array) + depth arena (int16) + occupancy arena (uint8)"""
+
+    def __init__(self, patches, depth, occ):
+        self.patches, self.depth, self.occ = patches, depth, occ
+
+    def depth_maps(self, i):
+        p = self.patches[i]
+        px = int(p["size_u"]) * int(p["size_v"])
+        o = int(p["depth_offset"])
+        shape = (int(p["size_v"]), int(p["size_u"]))
+        return self.depth[o:o + px].reshape(shape), self.depth[o + px:o + 2 * px].reshape(shape)
+
+    def occupancy(self, i):
+        p = self.patches[i]
+        nb = int(p["size_u0"]) * int(p["size_v0"])
+        o = int(p["occ_offset"])
+        return self.occ[o:o + nb].reshape(int(p["size_v0"]), int(p["size_u0"]))
+
+
+def _collect_patches(lib, prefix, h):
+    n = getattr(lib, prefix + "patches_count")(h)
+    de = getattr(lib, prefix + "patches_depth_elems")(h)
+    oe = getattr(lib, prefix + "patches_occ_elems")(h)
+    patches = np.zeros(n, dtype=PATCH_DTYPE)
+    depth = np.zeros(de, dtype=np.int16)
+    occ = np.zeros(oe, dtype=np.uint8)
+    getattr(lib, prefix + "patches_get")(h, patches.ctypes.data_as(C.c_void_p), ptr(depth, c_i16p), ptr(occ, c_u8p))
+    getattr(lib, prefix + "patches_free")(h)
+    return PatchSet(patches, depth, occ)
+
+
+def _decl_patch_api(lib, prefix):
+    getattr(lib, prefix + "patches_count").restype = C.c_int
+    getattr(lib, prefix + "patches_count").argtypes = [C.c_void_p]
+    for nme in ("patches_depth_elems", "patches_occ_elems"):
+        getattr(lib, prefix + nme).restype = C.c_size_t
+        getattr(lib, prefix + nme).argtypes = [C.c_void_p]
+    getattr(lib, prefix + "patches_get").restype = None
+    getattr(lib, prefix + "patches_get").argtypes = [C.c_void_p, C.c_void_p, c_i16p, c_u8p]
+    getattr(lib, prefix + "patches_free").restype = None
+    getattr(lib, prefix + "patches_free").argtypes = [C.c_void_p]
+
+
+# ------------------------------------------------------------------------------------------------ oracle
+class Oracle:
+    def __init__(self, path=ORACLE_SO):
+        L = self.lib = C.CDLL(path)
+        L.pcco_kdtree_build.restype = C.c_void_p
+        L.pcco_kdtree_build.argtypes = [c_i16p, C.c_size_t]
+        L.pcco_kdtree_free.argtypes = [C.c_void_p]
+        L.pcco_kdtree_vind.argtypes = [C.c_void_p, c_u32p]
+        L.pcco_knn.argtypes = [C.c_void_p, c_i16p, C.c_size_t, C.c_int, c_u32p, c_f32p]
+        L.pcco_radius.restype = C.c_size_t
+        L.pcco_radius.argtypes = [C.c_void_p, c_i16p, C.c_size_t, C.c_double, C.c_size_t, c_u64p, c_u32p, c_f32p]
+        L.pcco_normals.argtypes = [c_i16p, C.c_size_t, c_u32p, C.c_int, c_f64p]
+        L.pcco_orient_normals.argtypes = [c_i16p, C.c_size_t, c_u32p, C.c_int, c_f64p]
+        L.pcco_weight_normal.argtypes = [c_i16p, C.c_size_t, C.c_int, C.c_double, c_f64p]
+        L.pcco_initial_segmentation.argtypes = [c_f64p, C.c_size_t, c_f64p, c_u8p]
+        L.pcco_refine_segmentation.argtypes = [c_i16p, c_f64p, C.c_size_t, C.POINTER(SegParams), c_u8p]
+        L.pcco_segment_patches.restype = C.c_void_p
+        L.pcco_segment_patches.argtypes = [c_i16p, c_u8p, C.c_size_t, c_u32p, C.c_int, c_u8p, C.POINTER(SegParams)]
+        _decl_patch_api(L, "pcco_")
+
+    def vind(self, xyz):
+        xyz = _xyz(xyz)
+        t = self.lib.pcco_kdtree_build(ptr(xyz, c_i16p), len(xyz))
+        v = np.zeros(len(xyz), np.uint32)
+        self.lib.pcco_kdtree_vind(t, ptr(v, c_u32p))
+        self.lib.pcco_kdtree_free(t)
+        return v
+
+    def knn(self, xyz, q, k):
+        xyz, q = _xyz(xyz), _xyz(q)
+        t = self.lib.pcco_kdtree_build(ptr(xyz, c_i16p), len(xyz))
+        idx = np.zeros((len(q), k), np.uint32)
+        d = np.zeros((len(q), k), np.float32)
+        self.lib.pcco_knn(t, ptr(q, c_i16p), len(q), k, ptr(idx, c_u32p), ptr(d, c_f32p))
+        self.lib.pcco_kdtree_free(t)
+        return idx, d
+
+    def radius(self, xyz, q, r2, max_results):
+        xyz, q = _xyz(xyz), _xyz(q)
+        t = self.lib.pcco_kdtree_build(ptr(xyz, c_i16p), len(xyz))
+        off = np.zeros(len(q) + 1, np.uint64)
+        total = self.lib.pcco_radius(t, ptr(q, c_i16p), len(q), r2, max_results, ptr(off, c_u64p), None, None)
+        idx = np.zeros(total, np.uint32)
+        d = np.zeros(total, np.float32)
+        self.lib.pcco_radius(t, ptr(q, c_i16p), len(q), r2, max_results, ptr(off, c_u64p), ptr(idx, c_u32p), ptr(d, c_f32p))
+        self.lib.pcco_kdtree_free(t)
+        return off, idx, d
+
+    def normals(self, xyz, nbr, orient=True):
+        xyz = _xyz(xyz)
+        nbr = np.ascontiguousarray(nbr, np.uint32)
+        out = np.zeros((len(xyz), 3), np.float64)
+        self.lib.pcco_normals(ptr(xyz, c_i16p), len(xyz), ptr(nbr, c_u32p), nbr.shape[1], ptr(out, c_f64p))
+        if orient:
+            self.lib.pcco_orient_normals(ptr(xyz, c_i16p), len(xyz), ptr(nbr, c_u32p), nbr.shape[1], ptr(out, c_f64p))
+        return out
+
+    def weight_normal(self, xyz, bits, min_w=0.6):
+        xyz = _xyz(xyz)
+        w = np.zeros(3, np.float64)
+        self.lib.pcco_weight_normal(ptr(xyz, c_i16p), len(xyz), bits, min_w, ptr(w, c_f64p))
+        return w
+
+    def initial_segmentation(self, normals, w):
+        normals = np.ascontiguousarray(normals, np.float64)
+        w = np.ascontiguousarray(w, np.float64)
+        part = np.zeros(len(normals), np.uint8)
+        self.lib.pcco_initial_segmentation(ptr(normals, c_f64p), len(normals), ptr(w, c_f64p), ptr(part, c_u8p))
+        return part
+
+    def refine_segmentation(self, xyz, normals, partition, params):
+        xyz = _xyz(xyz)
+        normals = np.ascontiguousarray(normals, np.float64)
+        part = np.ascontiguousarray(partition, np.uint8).copy()
+        self.lib.pcco_refine_segmentation(ptr(xyz, c_i16p), ptr(normals, c_f64p), len(xyz), C.byref(params), ptr(part, c_u8p))
+        return part
+
+    def segment_patches(self, xyz, rgb, nbr, partition, params):
+        xyz = _xyz(xyz)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        nbr = np.ascontiguousarray(nbr, np.uint32)
+        part = np.ascontiguousarray(partition, np.uint8)
+        h = self.lib.pcco_segment_patches(ptr(xyz, c_i16p), ptr(rgb, c_u8p), len(xyz), ptr(nbr, c_u32p), nbr.shape[1],
+                                          ptr(part, c_u8p), C.byref(params))
+        return _collect_patches(self.lib, "pcco_", h)
+
+
+# --------------------------------------------------------------------------------------------- reference
+class Reference:
+    """The reference itself (compiled from /root/reference by oracle/Makefile)."""
+
+    def __init__(self, path=REF_SO):
+        L = self.lib = C.CDLL(path)
+        L.ref_knn.argtypes = [c_i16p, C.c_size_t, c_i16p, C.c_size_t, C.c_int, c_u32p, c_f32p]
+        L.ref_radius.restype = C.c_size_t
+        L.ref_radius.argtypes = [c_i16p, C.c_size_t, c_i16p, C.c_size_t, C.c_double, C.c_size_t, c_u64p, c_u32p, c_f32p]
+        L.ref_normals.argtypes = [c_i16p, C.c_size_t, C.c_int, C.c_int, c_f64p]
+        L.ref_weight_normal.argtypes = [c_i16p, C.c_size_t, C.c_int, C.c_double, c_f64p]
+        L.ref_segment_frame.restype = C.c_void_p
+        L.ref_segment_frame.argtypes = [c_i16p, c_u8p, C.c_size_t, C.POINTER(SegParams), c_f64p, c_u8p, c_u8p, c_f64p]
+        _decl_patch_api(L, "ref_")
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def knn(self, xyz, q, k):
+        xyz, q = _xyz(xyz), _xyz(q)
+        idx = np.zeros((len(q), k), np.uint32)
+        d = np.zeros((len(q), k), np.float32)
+        self.lib.ref_knn(ptr(xyz, c_i16p), len(xyz), ptr(q, c_i16p), len(q), k, ptr(idx, c_u32p), ptr(d, c_f32p))
+        return idx, d
+
+    def radius(self, xyz, q, r2, max_results):
+        xyz, q = _xyz(xyz), _xyz(q)
+        off = np.zeros(len(q) + 1, np.uint64)
+        total = self.lib.ref_radius(ptr(xyz, c_i16p), len(xyz), ptr(q, c_i16p), len(q), r2, max_results, ptr(off, c_u64p), None, None)
+        idx = np.zeros(total, np.uint32)
+        d = np.zeros(total, np.float32)
+        self.lib.ref_radius(ptr(xyz, c_i16p), len(xyz), ptr(q, c_i16p), len(q), r2, max_results, ptr(off, c_u64p), ptr(idx, c_u32p), ptr(d, c_f32p))
+        return off, idx, d
+
+    def normals(self, xyz, k=16, orient=True):
+        xyz = _xyz(xyz)
+        out = np.zeros((len(xyz), 3), np.float64)
+        self.lib.ref_normals(ptr(xyz, c_i16p), len(xyz), k, 1 if orient else 0, ptr(out, c_f64p))
+        return out
+
+    def weight_normal(self, xyz, bits, min_w=0.6):
+        xyz = _xyz(xyz)
+        w = np.zeros(3, np.float64)
+        self.lib.ref_weight_normal(ptr(xyz, c_i16p), len(xyz), bits, min_w, ptr(w, c_f64p))
+        return w
+
+    def segment_frame(self, xyz, rgb, params):
+        """returns dict(normals, partition0, partition1, patches: PatchSet, seconds)"""
+        xyz = _xyz(xyz)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        n = len(xyz)
+        normals = np.zeros((n, 3), np.float64)
+        p0 = np.zeros(n, np.uint8)
+        p1 = np.zeros(n, np.uint8)
+        sec = C.c_double(0)
+        h = self.lib.ref_segment_frame(ptr(xyz, c_i16p), ptr(rgb, c_u8p), n, C.byref(params), ptr(normals, c_f64p),
+                                       ptr(p0, c_u8p), ptr(p1, c_u8p), C.byref(sec))
+        return dict(normals=normals, partition0=p0, partition1=p1, patches=_collect_patches(self.lib, "ref_", h),
+                    seconds=sec.value)
