@@ -85,6 +85,24 @@ void        pccb200_destroy( pccb200_ctx* ctx );
 const char* pccb200_last_error( const pccb200_ctx* ctx );
 const char* pccb200_version( void );
 
+/* ---- stage-level entry points -------------------------------------------------------------------------
+ * Each replaces one public reference class used on its own by the tools (PccAppNormalGenerator uses PCCKdTree +
+ * PCCNormalsGenerator3 directly) and is what the parity tests drive. Host buffers in, host buffers out. */
+
+/* PCCKdTree::PCCKdTree + PCCKdTree::search (PccLibCommon/source/PCCKdTree.cpp:42-63): builds the nanoflann-
+ * shaped tree over xyz (n x 3 int16, |coord| < 2048) and answers nq k-NN queries (k in {1,8,16}).
+ * q == NULL means "the points themselves" (nq is then ignored). idx/dist2: row-major nq x k in nanoflann result
+ * order; rows are padded with 0xFFFFFFFF / -1 when n < k. dist2 may be NULL. */
+int pccb200_knn( pccb200_ctx* ctx, const int16_t* xyz, size_t n, const int16_t* q, size_t nq, int k, uint32_t* idx,
+                 float* dist2 );
+/* the tree's leaf order (nanoflann's vind after buildIndex); for tests of the builder */
+int pccb200_kdtree_order( pccb200_ctx* ctx, const int16_t* xyz, size_t n, uint32_t* vind );
+
+/* PCCNormalsGenerator3::compute (PccLibEncoder/source/PCCNormalsGenerator.cpp:61-70) with the parameters
+ * PCCPatchSegmenter3::compute passes (PCCPatchSegmenter.cpp:88-107): k-NN PCA normals (view point = origin),
+ * orientation 0 = none, 1 = spanning tree. normals: n x 3 doubles. */
+int pccb200_normals( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int k, int orientation, double* normals );
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,93 @@
+// common.cuh — shared device/host helpers for libpccb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pccb200.h"
+
+namespace pccb200 {
+
+struct CudaError {
+  cudaError_t code;
+  const char* file;
+  int         line;
+};
+
+#define PCC_CUDA( expr )                                                          \
+  do {                                                                            \
+    cudaError_t _e = ( expr );                                                    \
+    if ( _e != cudaSuccess ) throw ::pccb200::CudaError{ _e, __FILE__, __LINE__ }; \
+  } while ( 0 )
+
+#define PCC_LAUNCH_CHECK() PCC_CUDA( cudaGetLastError() )
+
+static inline int divUp( size_t a, size_t b ) { return int( ( a + b - 1 ) / b ); }
+
+// Grow-only device buffer; reused across frames so the steady state does no cudaMalloc.
+template <typename T>
+struct DevBuf {
+  T*     p   = nullptr;
+  size_t cap = 0;
+  DevBuf()   = default;
+  DevBuf( const DevBuf& )            = delete;
+  DevBuf& operator=( const DevBuf& ) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if ( p ) cudaFree( p );
+    p   = nullptr;
+    cap = 0;
+  }
+  // contents are NOT preserved
+  void reserve( size_t n ) {
+    if ( n <= cap ) return;
+    release();
+    size_t want = n + n / 8 + 64;
+    PCC_CUDA( cudaMalloc( &p, want * sizeof( T ) ) );
+    cap = want;
+  }
+  // contents preserved
+  void grow( size_t n, cudaStream_t s ) {
+    if ( n <= cap ) return;
+    size_t want = n + n / 2 + 64;
+    T*     q    = nullptr;
+    PCC_CUDA( cudaMalloc( &q, want * sizeof( T ) ) );
+    if ( p ) {
+      PCC_CUDA( cudaMemcpyAsync( q, p, cap * sizeof( T ), cudaMemcpyDeviceToDevice, s ) );
+      PCC_CUDA( cudaStreamSynchronize( s ) );
+      cudaFree( p );
+    }
+    p   = q;
+    cap = want;
+  }
+  operator T*() const { return p; }
+};
+
+// Pinned host staging buffer (grow-only).
+template <typename T>
+struct PinBuf {
+  T*     p   = nullptr;
+  size_t cap = 0;
+  ~PinBuf() {
+    if ( p ) cudaFreeHost( p );
+  }
+  void reserve( size_t n ) {
+    if ( n <= cap ) return;
+    if ( p ) cudaFreeHost( p );
+    PCC_CUDA( cudaMallocHost( &p, ( n + 64 ) * sizeof( T ) ) );
+    cap = n + 64;
+  }
+  operator T*() const { return p; }
+};
+
+// ---- device-wide exclusive scan of uint32 (scan.cu) ---------------------------------------------------
+// out[i] = sum_{j<i} in[j], out has n+1 entries (out[n] = total). tmp must hold scanTmpElems(n) uint32.
+size_t scanTmpElems( size_t n );
+void   exclusiveScanU32( const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp, cudaStream_t s );
+
+// Kernel timing record (filled when profiling is enabled on the ctx)
+struct StageTimer;
+
+}  // namespace pccb200

@@ -1,0 +1,21 @@
+// util.cu — small layout kernels.
+#include "stages.cuh"
+
+namespace pccb200 {
+
+namespace {
+// PCCPointSet3::positions_ is std::vector<PCCVector3<int16_t>> (6 B/point AoS, PCCPointSet.h:520-528);
+// on the device every point is one aligned 8-byte short4 so a point is a single load.
+__global__ void kPackXyz( const int16_t* __restrict__ in, int n, short4* __restrict__ out ) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i < n ) out[i] = make_short4( in[3 * size_t( i )], in[3 * size_t( i ) + 1], in[3 * size_t( i ) + 2], 0 );
+}
+}  // namespace
+
+void packXyz( const int16_t* xyz3, size_t n, short4* out, cudaStream_t s ) {
+  if ( n == 0 ) return;
+  kPackXyz<<<divUp( n, 256 ), 256, 0, s>>>( xyz3, int( n ), out );
+  PCC_LAUNCH_CHECK();
+}
+
+}  // namespace pccb200

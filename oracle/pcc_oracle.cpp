@@ -502,4 +502,347 @@ void pcco_initial_segmentation( const double* normals, size_t n, const double w[
   }
 }
 
+
+// ======================================================================================================
+// a6. Grid-based refinement (L/PccLibEncoder/source/PCCPatchSegmenter.cpp:1386-1561; voxel classes
+//     L/PccLibEncoder/include/PCCPatchSegmenter.h:430-510).
+// ======================================================================================================
+namespace {
+enum : uint8_t { NO_EDGE = 0x00, INDIRECT_EDGE = 0x01, M_DIRECT_EDGE = 0x10, S_DIRECT_EDGE = 0x11 };
+
+struct Voxel {
+  std::vector<uint32_t> pts;
+  uint16_t              score[6] = {0, 0, 0, 0, 0, 0};
+  uint8_t               edge = 0, ppi = 0, dirty = 1;
+
+  void recount( const uint8_t* partition ) {
+    for ( auto& s : score ) s = 0;
+    for ( uint32_t j : pts ) ++score[partition[j]];
+    if ( !dirty ) return;  // class and PPI are only re-derived for voxels whose points were re-labelled
+    if ( edge != S_DIRECT_EDGE ) {
+      int used = 0;
+      for ( auto s : score ) used += s != 0;
+      edge = used == 1 ? NO_EDGE : M_DIRECT_EDGE;
+    }
+    ppi   = uint8_t( std::max_element( score, score + 6 ) - score );
+    dirty = 0;
+  }
+};
+}  // namespace
+
+void pcco_refine_segmentation( const int16_t* xyz, const double* normals, size_t n, const pccb200_seg_params* prm,
+                               uint8_t* partition ) {
+  if ( n == 0 ) return;
+  static const double O[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};
+  const size_t        voxDim  = size_t( prm->voxel_dim_refine );
+  int16_t             geoMax  = xyz[0];
+  for ( size_t i = 0; i < 3 * n; ++i ) geoMax = std::max( geoMax, xyz[i] );
+  size_t geoRange = 1;
+  for ( size_t i = size_t( geoMax - 1 ); i != 0u; i >>= 1, geoRange <<= 1 ) {}
+  size_t voxShift = 0, gridShift = 0;
+  for ( size_t i = voxDim; i > 1; ++voxShift, i >>= 1 ) {}
+  const size_t gridDim = geoRange >> voxShift;
+  for ( size_t i = gridDim; i > 1; ++gridShift, i >>= 1 ) {}
+  const size_t half = voxDim >> 1;
+  auto         key  = [&]( size_t x, size_t y, size_t z ) { return x + ( y << gridShift ) + ( z << ( 2 * gridShift ) ); };
+
+  // voxels in order of first appearance; a voxel is identified by its key (keys of border voxels may alias)
+  std::vector<Voxel>                 vox;
+  std::vector<int16_t>               centers;
+  std::unordered_map<size_t, size_t> index;
+  for ( size_t i = 0; i < n; ++i ) {
+    const size_t x = ( size_t( xyz[3 * i] ) + half ) >> voxShift, y = ( size_t( xyz[3 * i + 1] ) + half ) >> voxShift,
+                 z = ( size_t( xyz[3 * i + 2] ) + half ) >> voxShift;
+    const size_t k  = key( x, y, z );
+    auto         it = index.find( k );
+    if ( it == index.end() ) {
+      it = index.emplace( k, vox.size() ).first;
+      vox.emplace_back();
+      centers.push_back( int16_t( x ) ), centers.push_back( int16_t( y ) ), centers.push_back( int16_t( z ) );
+    }
+    vox[it->second].pts.push_back( uint32_t( i ) );
+  }
+  const size_t V = vox.size();
+  // the reference re-looks each voxel up by the key of its centre: aliasing keys resolve to the same cell
+  std::vector<size_t> cell( V );
+  for ( size_t v = 0; v < V; ++v ) cell[v] = index[key( size_t( centers[3 * v] ), size_t( centers[3 * v + 1] ), size_t( centers[3 * v + 2] ) )];
+  for ( size_t v = 0; v < V; ++v ) {
+    Voxel& c = vox[cell[v]];
+    c.edge   = uint8_t( c.pts.size() ) == 1 ? S_DIRECT_EDGE : M_DIRECT_EDGE;
+    c.recount( partition );
+  }
+  // adjacency: voxels with centre distance^2 < (searchRadius >> shift), sorted by (distance, index)
+  Tree tree;
+  tree.build( centers.data(), V );
+  const double                       r2 = double( size_t( prm->search_radius_refine ) >> voxShift );
+  std::vector<std::vector<uint32_t>> adj( V ), near( V );
+  std::vector<double>                weight( V );
+  const size_t                       nearRange = voxDim >= 4 ? 1 : 2;
+  std::vector<std::pair<double, uint32_t>> found;
+  for ( size_t v = 0; v < V; ++v ) {
+    found.clear();
+    RadiusSet rs( r2, found );
+    tree.search( rs, &centers[3 * v] );
+    std::sort( found.begin(), found.end() );
+    if ( found.size() > 32767 ) found.resize( 32767 );
+    size_t nn = 0;
+    for ( auto& f : found ) {
+      const uint32_t o = f.second;
+      adj[v].push_back( o );
+      if ( size_t( std::abs( centers[3 * v] - centers[3 * o] ) ) <= nearRange &&
+           size_t( std::abs( centers[3 * v + 1] - centers[3 * o + 1] ) ) <= nearRange &&
+           size_t( std::abs( centers[3 * v + 2] - centers[3 * o + 2] ) ) <= nearRange )
+        near[v].push_back( o );
+      nn += uint8_t( vox[cell[o]].pts.size() );
+      if ( nn >= size_t( prm->max_nn_count_refine ) ) break;
+    }
+    weight[v] = prm->lambda_refine / double( nn );
+  }
+  for ( int iter = 0; iter < std::max( 1, prm->iteration_count_refine ); ++iter ) {
+    for ( size_t v = 0; v < V; ++v ) {
+      Voxel&        c        = vox[cell[v]];
+      const uint8_t edgeHere = c.edge;
+      if ( edgeHere == NO_EDGE ) continue;
+      uint16_t smooth[6] = {0, 0, 0, 0, 0, 0};
+      for ( uint32_t o : adj[v] )
+        for ( int k = 0; k < 6; ++k ) smooth[k] = uint16_t( smooth[k] + vox[cell[o]].score[k] );
+      const size_t top = size_t( std::max_element( smooth, smooth + 6 ) - smooth );
+      for ( uint32_t o : near[v] ) {
+        Voxel& d = vox[cell[o]];
+        if ( d.edge == NO_EDGE && d.ppi != top ) d.edge = INDIRECT_EDGE;
+      }
+      if ( edgeHere != M_DIRECT_EDGE ) {
+        int used = 0;
+        for ( auto s : smooth ) used += s != 0;
+        if ( used == 1 && smooth[c.ppi] > 0 ) continue;
+      }
+      for ( uint32_t j : c.pts ) {
+        double sc[6];
+        for ( int k = 0; k < 6; ++k ) sc[k] = dot3( normals + 3 * size_t( j ), O[k] ) + weight[v] * double( smooth[k] );
+        partition[j] = uint8_t( std::max_element( sc, sc + 6 ) - sc );
+      }
+      c.dirty = 1;
+    }
+    for ( size_t v = 0; v < V; ++v ) vox[cell[v]].recount( partition );
+  }
+}
+
+// ======================================================================================================
+// a7–a11. Patch segmentation (L/PccLibEncoder/source/PCCPatchSegmenter.cpp:537-1320, CTC path: no EOM,
+//         6 projection planes, no partitioning/expansion/gradient separation), resampling (:362-470).
+// ======================================================================================================
+namespace {
+struct OPatch {
+  pccb200_patch        m;
+  std::vector<int16_t> depth[2];
+  std::vector<uint8_t> occ;
+};
+struct OPatchList {
+  std::vector<OPatch> patches;
+};
+const int kViewAxes[6][4] = {{0, 2, 1, 0}, {1, 2, 0, 0}, {2, 0, 1, 0}, {0, 2, 1, 1}, {1, 2, 0, 1}, {2, 0, 1, 1}};  // normal,tangent,bitangent,mode
+const int16_t kInfDepth   = 32767;
+}  // namespace
+
+void* pcco_segment_patches( const int16_t* xyz, const uint8_t* rgb, size_t n, const uint32_t* nbr, int k,
+                            const uint8_t* partition, const pccb200_seg_params* prm ) {
+  OPatchList*          out = new OPatchList();
+  std::vector<double>  rawDist( n, std::numeric_limits<double>::max() );
+  std::vector<uint32_t> raw( n );
+  for ( size_t i = 0; i < n; ++i ) raw[i] = uint32_t( i );
+  std::vector<int16_t> resampled;  // x,y,z triples
+  const int            occRes = prm->occupancy_resolution;
+  const int            minLevel = prm->min_level, thickness = prm->surface_thickness;
+  while ( !raw.empty() ) {
+    // ---- connected components over the directed k-NN graph, seeds in ascending index among far raw points
+    std::vector<uint8_t> flag( n, 0 );
+    for ( uint32_t i : raw ) flag[i] = 1;
+    std::vector<std::vector<uint32_t>> comps;
+    std::vector<uint32_t>              stack;
+    for ( uint32_t i : raw ) {
+      if ( !flag[i] || !( rawDist[i] > prm->max_allowed_dist2_raw_detection ) ) continue;
+      flag[i] = 0;
+      comps.emplace_back();
+      auto&         cc = comps.back();
+      const uint8_t cl = partition[i];
+      stack.push_back( i ), cc.push_back( i );
+      while ( !stack.empty() ) {
+        const uint32_t cur = stack.back();
+        stack.pop_back();
+        const uint32_t* row = nbr + size_t( cur ) * k;
+        for ( int j = 0; j < k && row[j] != 0xFFFFFFFFu; ++j ) {
+          const uint32_t o = row[j];
+          if ( partition[o] == cl && flag[o] ) flag[o] = 0, stack.push_back( o ), cc.push_back( o );
+        }
+      }
+      if ( cc.size() < size_t( prm->min_point_count_per_cc ) ) comps.pop_back();
+    }
+    if ( comps.empty() ) break;
+    for ( auto& cc : comps ) {
+      out->patches.emplace_back();
+      OPatch&        P = out->patches.back();
+      pccb200_patch& m = P.m;
+      std::memset( &m, 0, sizeof( m ) );
+      m.index   = int32_t( out->patches.size() - 1 );
+      m.view_id = partition[cc[0]];
+      m.normal_axis = kViewAxes[m.view_id][0], m.tangent_axis = kViewAxes[m.view_id][1];
+      m.bitangent_axis = kViewAxes[m.view_id][2], m.projection_mode = kViewAxes[m.view_id][3];
+      m.u0 = m.v0 = m.orientation = -1;
+      const int na = m.normal_axis, ta = m.tangent_axis, ba = m.bitangent_axis, mode = m.projection_mode;
+      const int dir = 1 - 2 * mode;
+      auto      C   = [&]( uint32_t i, int axis ) { return int( xyz[3 * size_t( i ) + axis] ); };
+      if ( prm->enable_patch_splitting ) {  // keep the part within maxPatchSize of the minimum corner
+        int minU = 32767, minV = 32767;
+        for ( uint32_t i : cc ) minU = std::min( minU, C( i, ta ) ), minV = std::min( minV, C( i, ba ) );
+        std::vector<uint32_t> kept;
+        for ( uint32_t i : cc )
+          if ( C( i, ta ) - minU < prm->max_patch_size && C( i, ba ) - minV < prm->max_patch_size ) kept.push_back( i );
+        cc.swap( kept );
+        if ( cc.empty() ) continue;  // (the reference leaves an empty patch in the list here as well)
+      }
+      int mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {0, 0, 0};
+      for ( uint32_t i : cc )
+        for ( int a = 0; a < 3; ++a ) mn[a] = std::min( mn[a], C( i, a ) ), mx[a] = std::max( mx[a], C( i, a ) );
+      m.size_u = 1 + mx[ta] - mn[ta], m.size_v = 1 + mx[ba] - mn[ba];
+      m.u1 = mn[ta], m.v1 = mn[ba];
+      const size_t px = size_t( m.size_u ) * m.size_v;
+      P.depth[0].assign( px, kInfDepth );
+      std::vector<uint32_t> owner( px, 0xFFFFFFFFu );
+      int                   maxU = 0, maxV = 0, extreme = mode == 0 ? kInfDepth : 0;
+      for ( uint32_t i : cc ) {  // depth0 = nearest (mode 0) / farthest (mode 1) point per pixel
+        const int    d = C( i, na ), u = C( i, ta ) - m.u1, v = C( i, ba ) - m.v1;
+        const size_t p = size_t( v ) * m.size_u + u;
+        const bool   better = mode == 0 ? P.depth[0][p] > d : ( P.depth[0][p] == kInfDepth || P.depth[0][p] < d );
+        if ( !better ) continue;
+        P.depth[0][p] = int16_t( d ), owner[p] = i;
+        maxU = std::max( maxU, u ), maxV = std::max( maxV, v );
+        extreme = mode == 0 ? std::min( extreme, d ) : std::max( extreme, d );
+      }
+      m.d1 = mode == 0 ? ( extreme / minLevel ) * minLevel : int( std::ceil( double( extreme ) / double( minLevel ) ) ) * minLevel;
+      m.size_u0 = maxU / occRes + 1, m.size_v0 = maxV / occRes + 1;
+      m.size_2d_x = int( std::ceil( double( maxU + 1 ) / double( prm->quantizer_size_x ) ) * prm->quantizer_size_x );
+      m.size_2d_y = int( std::ceil( double( maxV + 1 ) / double( prm->quantizer_size_y ) ) * prm->quantizer_size_y );
+      P.occ.assign( size_t( m.size_u0 ) * m.size_v0, 0 );
+      // per-block peak filter
+      std::vector<int16_t> peak( P.occ.size(), mode == 0 ? kInfDepth : int16_t( 0 ) );
+      for ( int v = 0; v < m.size_v; ++v )
+        for ( int u = 0; u < m.size_u; ++u ) {
+          const int16_t d = P.depth[0][size_t( v ) * m.size_u + u];
+          if ( d == kInfDepth ) continue;
+          int16_t& pk = peak[size_t( v / occRes ) * m.size_u0 + u / occRes];
+          pk          = mode == 0 ? std::min( pk, d ) : std::max( pk, d );
+        }
+      for ( int v = 0; v < m.size_v; ++v )
+        for ( int u = 0; u < m.size_u; ++u ) {
+          const size_t  p = size_t( v ) * m.size_u + u;
+          const int16_t d = P.depth[0][p];
+          if ( d == kInfDepth ) continue;
+          const int16_t pk = peak[size_t( v / occRes ) * m.size_u0 + u / occRes];
+          const int16_t a  = int16_t( std::abs( d - pk ) );
+          const int16_t b  = int16_t( thickness + dir * d );
+          const int16_t c  = int16_t( dir * m.d1 + prm->max_allowed_depth );
+          if ( a > 32 || b > c ) P.depth[0][p] = kInfDepth, owner[p] = 0xFFFFFFFFu;
+        }
+      // depth1: farthest point within surfaceThickness of depth0 whose colour is close to the depth0 point's
+      P.depth[1] = P.depth[0];
+      if ( thickness > 0 )
+        for ( uint32_t i : cc ) {
+          const int     d = C( i, na ), u = C( i, ta ) - m.u1, v = C( i, ba ) - m.v1;
+          const size_t  p  = size_t( v ) * m.size_u + u;
+          const int16_t d0 = P.depth[0][p];
+          if ( !( d0 < kInfDepth ) ) continue;
+          const int16_t  delta = int16_t( dir * ( d - d0 ) );
+          const uint8_t *ci = rgb + 3 * size_t( i ), *c0 = rgb + 3 * size_t( owner[p] );
+          const bool similar = std::abs( int( c0[0] ) - ci[0] ) < 128 && std::abs( int( c0[1] ) - ci[1] ) < 128 &&
+                               std::abs( int( c0[2] ) - ci[2] ) < 128;
+          if ( delta <= thickness && delta >= 0 && similar && dir * ( d - P.depth[1][p] ) > 0 ) P.depth[1][p] = int16_t( d );
+        }
+      // resample: D0 then D1 point per occupied pixel (raster order), depths re-based to d1
+      int sizeD = 0, d0Count = 0;
+      for ( int v = 0; v < m.size_v; ++v )
+        for ( int u = 0; u < m.size_u; ++u ) {
+          const size_t p = size_t( v ) * m.size_u + u;
+          if ( !( P.depth[0][p] < kInfDepth ) ) continue;
+          P.occ[size_t( v / occRes ) * m.size_u0 + u / occRes] = 1;
+          for ( int map = 0; map < 2; ++map ) {
+            int16_t q[3];
+            q[na] = P.depth[map][p], q[ta] = int16_t( u + m.u1 ), q[ba] = int16_t( v + m.v1 );
+            resampled.insert( resampled.end(), q, q + 3 );
+          }
+          ++d0Count;
+          for ( int map = 0; map < 2; ++map ) {
+            P.depth[map][p] = int16_t( dir * ( P.depth[map][p] - int16_t( m.d1 ) ) );
+            sizeD           = std::max( sizeD, int( P.depth[map][p] ) );
+          }
+        }
+      m.d0_count     = d0Count;
+      m.size_d_pixel = sizeD;
+      const int bd   = std::min( prm->geometry_bitdepth_3d, prm->geometry_bitdepth_2d );
+      sizeD          = std::min( ( 1 << bd ) - 1, sizeD );
+      const int lv   = int( std::log2( double( minLevel ) ) );
+      int       qd   = sizeD == 0 ? 0 : ( ( sizeD - 1 ) / minLevel + 1 );
+      qd             = std::min( qd, ( 1 << ( bd - lv ) ) - 1 );
+      m.size_d       = qd == 0 ? 0 : qd * minLevel - 1;
+    }
+    // ---- residual: points farther than sqrt(selection) from everything resampled so far stay raw
+    Tree rt;
+    rt.build( resampled.data(), resampled.size() / 3 );
+    raw.clear();
+    for ( size_t i = 0; i < n; ++i ) {
+      uint32_t id;
+      double   d;
+      KnnSet   rs( 1, &id, &d );
+      rt.search( rs, xyz + 3 * i );
+      rawDist[i] = d;
+      if ( d > prm->max_allowed_dist2_raw_selection ) raw.push_back( uint32_t( i ) );
+    }
+  }
+  return out;
+}
+
+int    pcco_patches_count( void* h ) { return int( static_cast<OPatchList*>( h )->patches.size() ); }
+size_t pcco_patches_depth_elems( void* h ) {
+  size_t s = 0;
+  for ( auto& p : static_cast<OPatchList*>( h )->patches ) s += 2 * size_t( p.m.size_u ) * p.m.size_v;
+  return s;
+}
+size_t pcco_patches_occ_elems( void* h ) {
+  size_t s = 0;
+  for ( auto& p : static_cast<OPatchList*>( h )->patches ) s += size_t( p.m.size_u0 ) * p.m.size_v0;
+  return s;
+}
+void pcco_patches_get( void* h, pccb200_patch* out, int16_t* depth, uint8_t* occ ) {
+  int64_t dOff = 0, oOff = 0;
+  size_t  i    = 0;
+  for ( auto& p : static_cast<OPatchList*>( h )->patches ) {
+    out[i]              = p.m;
+    out[i].depth_offset = dOff, out[i].occ_offset = oOff;
+    ++i;
+    const size_t px = size_t( p.m.size_u ) * p.m.size_v;
+    for ( int m = 0; m < 2; ++m )
+      for ( size_t j = 0; j < px; ++j ) depth[dOff + m * px + j] = j < p.depth[m].size() ? p.depth[m][j] : int16_t( 0 );
+    dOff += 2 * px;
+    std::copy( p.occ.begin(), p.occ.end(), occ + oOff );
+    oOff += p.occ.size();
+  }
+}
+void pcco_patches_free( void* h ) { delete static_cast<OPatchList*>( h ); }
+
+void* pcco_segment_frame( const int16_t* xyz, const uint8_t* rgb, size_t n, const pccb200_seg_params* p ) {
+  if ( n == 0 ) return new OPatchList();
+  const int             k = p->nn_normal_estimation;
+  Tree                  t;
+  t.build( xyz, n );
+  std::vector<uint32_t> nbr( n * k );
+  std::vector<float>    d( n * k );
+  pcco_knn( &t, xyz, n, k, nbr.data(), d.data() );
+  std::vector<double> normals( 3 * n );
+  pcco_normals( xyz, n, nbr.data(), k, normals.data() );
+  if ( p->normal_orientation == 1 ) pcco_orient_normals( xyz, n, nbr.data(), k, normals.data() );
+  std::vector<uint8_t> part( n );
+  pcco_initial_segmentation( normals.data(), n, p->weight_normal, part.data() );
+  pcco_refine_segmentation( xyz, normals.data(), n, p, part.data() );
+  return pcco_segment_patches( xyz, rgb, n, nbr.data(), p->max_nn_count_patch_seg, part.data(), p );
+}
+
 }  // extern "C"

@@ -128,9 +128,31 @@ def _decl_patch_api(lib, prefix):
 
 
 # ------------------------------------------------------------------------------------------------ oracle
+class _Lazy:
+    """CDLL wrapper: declaring the signature of a symbol that is not built yet is not an error until it is called."""
+
+    class _Missing:
+        def __init__(self, name):
+            self.name = name
+
+        def __call__(self, *a):
+            raise RuntimeError("symbol %s is not exported by the library" % self.name)
+
+    def __init__(self, path):
+        object.__setattr__(self, "_dll", C.CDLL(path))
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._dll, name)
+        except AttributeError:
+            m = _Lazy._Missing(name)
+            object.__setattr__(self, name, m)
+            return m
+
+
 class Oracle:
     def __init__(self, path=ORACLE_SO):
-        L = self.lib = C.CDLL(path)
+        L = self.lib = _Lazy(path)
         L.pcco_kdtree_build.restype = C.c_void_p
         L.pcco_kdtree_build.argtypes = [c_i16p, C.c_size_t]
         L.pcco_kdtree_free.argtypes = [C.c_void_p]
@@ -274,3 +296,55 @@ class Reference:
                                        ptr(p0, c_u8p), ptr(p1, c_u8p), C.byref(sec))
         return dict(normals=normals, partition0=p0, partition1=p1, patches=_collect_patches(self.lib, "ref_", h),
                     seconds=sec.value)
+
+
+# ----------------------------------------------------------------------------------------------- product
+class Product:
+    """libpccb200.so through its C ABI (include/pccb200.h). Needs a CUDA device; there is no CPU path."""
+
+    def __init__(self, device=0, path=PRODUCT_SO):
+        if not os.path.exists(path):
+            raise RuntimeError("libpccb200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = self.lib = C.CDLL(path)
+        L.pccb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.pccb200_destroy.argtypes = [C.c_void_p]
+        L.pccb200_last_error.restype = C.c_char_p
+        L.pccb200_last_error.argtypes = [C.c_void_p]
+        L.pccb200_version.restype = C.c_char_p
+        L.pccb200_knn.argtypes = [C.c_void_p, c_i16p, C.c_size_t, c_i16p, C.c_size_t, C.c_int, c_u32p, c_f32p]
+        L.pccb200_kdtree_order.argtypes = [C.c_void_p, c_i16p, C.c_size_t, c_u32p]
+        L.pccb200_normals.argtypes = [C.c_void_p, c_i16p, C.c_size_t, C.c_int, C.c_int, c_f64p]
+        self.ctx = C.c_void_p()
+        rc = L.pccb200_create(device, C.byref(self.ctx))
+        if rc != 0:
+            raise RuntimeError("pccb200_create failed with %d (no CUDA device? the product has no CPU fallback)" % rc)
+
+    def close(self):
+        if self.ctx:
+            self.lib.pccb200_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("pccb200 error %d: %s" % (rc, self.lib.pccb200_last_error(self.ctx).decode()))
+
+    def knn(self, xyz, q, k):
+        xyz = _xyz(xyz)
+        nq = len(xyz) if q is None else len(q)
+        idx = np.zeros((nq, k), np.uint32)
+        d = np.zeros((nq, k), np.float32)
+        qp = None if q is None else ptr(_xyz(q), c_i16p)
+        self._check(self.lib.pccb200_knn(self.ctx, ptr(xyz, c_i16p), len(xyz), qp, nq, k, ptr(idx, c_u32p), ptr(d, c_f32p)))
+        return idx, d
+
+    def vind(self, xyz):
+        xyz = _xyz(xyz)
+        v = np.zeros(len(xyz), np.uint32)
+        self._check(self.lib.pccb200_kdtree_order(self.ctx, ptr(xyz, c_i16p), len(xyz), ptr(v, c_u32p)))
+        return v
+
+    def normals(self, xyz, k=16, orient=False):
+        xyz = _xyz(xyz)
+        out = np.zeros((len(xyz), 3), np.float64)
+        self._check(self.lib.pccb200_normals(self.ctx, ptr(xyz, c_i16p), len(xyz), k, 1 if orient else 0, ptr(out, c_f64p)))
+        return out
