@@ -687,7 +687,7 @@ void* pcco_segment_patches( const int16_t* xyz, const uint8_t* rgb, size_t n, co
       m.view_id = partition[cc[0]];
       m.normal_axis = kViewAxes[m.view_id][0], m.tangent_axis = kViewAxes[m.view_id][1];
       m.bitangent_axis = kViewAxes[m.view_id][2], m.projection_mode = kViewAxes[m.view_id][3];
-      m.u0 = m.v0 = m.orientation = -1;
+      m.u0 = m.v0 = m.orientation = 0;  // PCCPatch defaults before packing
       const int na = m.normal_axis, ta = m.tangent_axis, ba = m.bitangent_axis, mode = m.projection_mode;
       const int dir = 1 - 2 * mode;
       auto      C   = [&]( uint32_t i, int axis ) { return int( xyz[3 * size_t( i ) + axis] ); };
