@@ -103,6 +103,23 @@ int pccb200_kdtree_order( pccb200_ctx* ctx, const int16_t* xyz, size_t n, uint32
  * orientation 0 = none, 1 = spanning tree. normals: n x 3 doubles. */
 int pccb200_normals( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int k, int orientation, double* normals );
 
+/* PCCPatchSegmenter3::compute (PccLibEncoder/source/PCCPatchSegmenter.cpp:53-150), CTC path: k-d tree, normals +
+ * orientation, initial segmentation, grid-based refinement, patch segmentation (a1..a11 of SURVEY.md §8a) for ONE
+ * frame. rgb is n x 3 uint8 (the D1 colour gate reads it). The optional outputs expose the intermediate results
+ * the reference keeps in PCCNormalsGenerator3::normals_ and `partition` (before / after refinement); pass NULL to
+ * skip them. The patch list is returned as an opaque handle (pccb200_patches_*). */
+typedef struct pccb200_patchlist pccb200_patchlist;
+int    pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* rgb, size_t n,
+                              const pccb200_seg_params* params, double* normals, uint8_t* partition_initial,
+                              uint8_t* partition_refined, pccb200_patchlist** out );
+int    pccb200_patches_count( const pccb200_patchlist* pl );
+size_t pccb200_patches_depth_elems( const pccb200_patchlist* pl );
+size_t pccb200_patches_occ_elems( const pccb200_patchlist* pl );
+/* copies patch records, both depth maps of every patch (int16, re-based to d1, 32767 = empty) and the block
+ * occupancy (uint8) into caller buffers sized by the three calls above */
+int    pccb200_patches_get( const pccb200_patchlist* pl, pccb200_patch* patches, int16_t* depth_arena, uint8_t* occ_arena );
+void   pccb200_patches_free( pccb200_patchlist* pl );
+
 #ifdef __cplusplus
 }
 #endif

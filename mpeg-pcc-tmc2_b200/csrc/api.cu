@@ -1,5 +1,6 @@
 // api.cu — the C ABI (include/pccb200.h). Host-side orchestration only; all point/pixel work is in kernels.
 #include <mutex>
+#include <algorithm>
 #include <new>
 
 #include "stages.cuh"
@@ -17,6 +18,17 @@ struct pccb200_ctx {
   DevBuf<uint32_t> nbr;
   DevBuf<float>    nbrDist;
   DevBuf<double>   normals;
+  DevBuf<uint8_t>  rgbRaw, partition;
+  DevBuf<uchar4>   rgb4;
+  OrientScratch    orient;
+  RefineScratch    refine;
+  PatchScratch     patch;
+};
+
+struct pccb200_patchlist {
+  std::vector<pccb200_patch> patches;
+  std::vector<int16_t>       depth;
+  std::vector<uint8_t>       occ;
 };
 
 namespace {
@@ -126,7 +138,7 @@ int pccb200_kdtree_order( pccb200_ctx* ctx, const int16_t* xyz, size_t n, uint32
 int pccb200_normals( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int k, int orientation, double* normals ) {
   return guarded( ctx, [&]() -> int {
     if ( !xyz || !normals || k != 16 ) return PCCB200_ERR_BAD_ARG;
-    if ( orientation != 0 ) return PCCB200_ERR_UNSUPPORTED;
+    if ( orientation != 0 && orientation != 1 ) return PCCB200_ERR_UNSUPPORTED;
     if ( n == 0 ) return PCCB200_OK;
     uploadXyz( ctx, xyz, n, ctx->xyz4 );
     kdBuild( ctx->tree, ctx->xyz4, n, ctx->stream );
@@ -134,10 +146,64 @@ int pccb200_normals( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int k, int 
     ctx->normals.reserve( 3 * n );
     kdKnn( ctx->tree, ctx->xyz4, n, ctx->tree.vind, k, ctx->nbr, nullptr, ctx->stream );
     computeNormals( ctx->xyz4, ctx->nbr, k, n, ctx->normals, ctx->stream );
+    if ( orientation == 1 ) orientNormals( ctx->orient, ctx->xyz4, ctx->nbr, k, n, ctx->normals, ctx->stream );
     PCC_CUDA( cudaMemcpyAsync( normals, ctx->normals, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
     PCC_CUDA( cudaStreamSynchronize( ctx->stream ) );
     return PCCB200_OK;
   } );
 }
+
+int pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* rgb, size_t n, const pccb200_seg_params* prm,
+                           double* normals, uint8_t* part0, uint8_t* part1, pccb200_patchlist** out ) {
+  return guarded( ctx, [&]() -> int {
+    if ( !xyz || !rgb || !prm || !out ) return PCCB200_ERR_BAD_ARG;
+    if ( prm->nn_normal_estimation != 16 || prm->max_nn_count_patch_seg != 16 || prm->geometry_bitdepth_3d > 12 ||
+         ( prm->normal_orientation != 0 && prm->normal_orientation != 1 ) )
+      return PCCB200_ERR_UNSUPPORTED;
+    *out = nullptr;
+    pccb200_patchlist* pl = new pccb200_patchlist();
+    if ( n == 0 ) {
+      *out = pl;
+      return PCCB200_OK;
+    }
+    cudaStream_t s = ctx->stream;
+    const int    k = 16;
+    uploadXyz( ctx, xyz, n, ctx->xyz4 );
+    ctx->rgbRaw.reserve( 3 * n ), ctx->rgb4.reserve( n ), ctx->partition.reserve( n );
+    PCC_CUDA( cudaMemcpyAsync( ctx->rgbRaw, rgb, 3 * n, cudaMemcpyHostToDevice, s ) );
+    packRgb( ctx->rgbRaw, n, ctx->rgb4, s );
+    kdBuild( ctx->tree, ctx->xyz4, n, s );
+    ctx->nbr.reserve( n * k + 1 ), ctx->normals.reserve( 3 * n );
+    kdKnn( ctx->tree, ctx->xyz4, n, ctx->tree.vind, k, ctx->nbr, nullptr, s );
+    computeNormals( ctx->xyz4, ctx->nbr, k, n, ctx->normals, s );
+    if ( prm->normal_orientation == 1 ) orientNormals( ctx->orient, ctx->xyz4, ctx->nbr, k, n, ctx->normals, s );
+    if ( normals ) PCC_CUDA( cudaMemcpyAsync( normals, ctx->normals, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, s ) );
+    initialSegmentation( ctx->normals, n, prm->weight_normal, ctx->partition, s );
+    if ( part0 ) PCC_CUDA( cudaMemcpyAsync( part0, ctx->partition, n, cudaMemcpyDeviceToHost, s ) );
+    refineSegmentation( ctx->refine, ctx->xyz4, ctx->normals, n, *prm, ctx->partition, s );
+    if ( part1 ) PCC_CUDA( cudaMemcpyAsync( part1, ctx->partition, n, cudaMemcpyDeviceToHost, s ) );
+    PatchResult res;
+    segmentPatches( ctx->patch, res, ctx->xyz4, ctx->rgb4, ctx->nbr, k, ctx->partition, n, *prm, s );
+    pl->patches = res.patches;
+    pl->depth.resize( res.depthElems ), pl->occ.resize( res.occElems );
+    if ( res.depthElems ) PCC_CUDA( cudaMemcpyAsync( pl->depth.data(), res.depth, res.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, s ) );
+    if ( res.occElems ) PCC_CUDA( cudaMemcpyAsync( pl->occ.data(), res.occ, res.occElems, cudaMemcpyDeviceToHost, s ) );
+    PCC_CUDA( cudaStreamSynchronize( s ) );
+    *out = pl;
+    return PCCB200_OK;
+  } );
+}
+
+int    pccb200_patches_count( const pccb200_patchlist* pl ) { return pl ? int( pl->patches.size() ) : 0; }
+size_t pccb200_patches_depth_elems( const pccb200_patchlist* pl ) { return pl ? pl->depth.size() : 0; }
+size_t pccb200_patches_occ_elems( const pccb200_patchlist* pl ) { return pl ? pl->occ.size() : 0; }
+int    pccb200_patches_get( const pccb200_patchlist* pl, pccb200_patch* patches, int16_t* depth, uint8_t* occ ) {
+  if ( !pl ) return PCCB200_ERR_BAD_ARG;
+  if ( patches ) std::copy( pl->patches.begin(), pl->patches.end(), patches );
+  if ( depth ) std::copy( pl->depth.begin(), pl->depth.end(), depth );
+  if ( occ ) std::copy( pl->occ.begin(), pl->occ.end(), occ );
+  return PCCB200_OK;
+}
+void pccb200_patches_free( pccb200_patchlist* pl ) { delete pl; }
 
 }  // extern "C"

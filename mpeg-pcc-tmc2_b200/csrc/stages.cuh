@@ -9,7 +9,56 @@ namespace pccb200 {
 void computeNormals( const short4* pts, const uint32_t* nbr, int k, size_t n, double* normals, cudaStream_t s );
 void initialSegmentation( const double* normals, size_t n, const double w[3], uint8_t* partition, cudaStream_t s );
 
+// orient.cu
+struct OrientScratch {
+  DevBuf<uint32_t> nbrSorted, relBits, idsA, idsB, rankRel, best;
+  DevBuf<uint64_t> keysA, keysB, L0;
+  DevBuf<uint2>    byRank;
+  DevBuf<uint8_t>  flip, cubTmp;
+  DevBuf<unsigned> counter;
+};
+void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, size_t n, double* normals, cudaStream_t s );
+
+// refine.cu
+struct RefineScratch {
+  DevBuf<int>                ints, grid, offsets;
+  DevBuf<uint32_t>           keysA, keysB, idsA, idsSorted, head, headScan, scanTmp;
+  DevBuf<uint32_t>           runStart, runFirst, runId, runFirstSorted, order, voxStart, voxCount, runToVox;
+  DevBuf<short4>             centers;
+  DevBuf<uint32_t>           adjOff, adjLen, adjData, nearData, list;
+  DevBuf<uint8_t>            nearLen, edge, ppi, dirty, mark, active, cubTmp;
+  DevBuf<double>             weight;
+  DevBuf<uint16_t>           score, smooth;
+  DevBuf<unsigned long long> cursor;
+  DevBuf<unsigned>           count;
+  int                        offsetsR2 = -1, numOffsets = 0;
+};
+void refineSegmentation( RefineScratch& sc, const short4* pts, const double* normals, size_t n, const pccb200_seg_params& prm,
+                         uint8_t* partition, cudaStream_t s );
+
+// patches.cu
+struct PatchScratch {
+  DevBuf<uint8_t>            raw, minD2, seedView;
+  DevBuf<uint16_t>           mutual;
+  DevBuf<uint32_t>           parent, compLabel, compSize, label, kept, keptScan, scanTmp, bitmap, owner, seedIdx;
+  DevBuf<int>                member, ints, d0, d1, peak;
+  DevBuf<unsigned long long> keys;
+  DevBuf<long long>          depthOff, occOff;
+  DevBuf<char>               stats, devPatches, counters;  // typed inside patches.cu
+};
+struct PatchResult {
+  std::vector<pccb200_patch> patches;
+  DevBuf<int16_t>            depth;  // arena on the device
+  DevBuf<uint8_t>            occ;
+  size_t                     depthElems = 0, occElems = 0;
+  int                        outerIterations = 0;
+};
+void packRgb( const uint8_t* rgb3, size_t n, uchar4* out, cudaStream_t s );
+void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, const uchar4* rgb, const uint32_t* nbr, int k,
+                     const uint8_t* partition, size_t n, const pccb200_seg_params& prm, cudaStream_t s );
+
 // util.cu
+void gatherU8( const uint8_t* src, const uint32_t* idx, size_t n, uint8_t* dst, cudaStream_t s );
 void packXyz( const int16_t* xyz3, size_t n, short4* out, cudaStream_t s );  // device int16 AoS (n x 3) -> short4
 
 }  // namespace pccb200

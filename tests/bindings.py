@@ -314,6 +314,15 @@ class Product:
         L.pccb200_knn.argtypes = [C.c_void_p, c_i16p, C.c_size_t, c_i16p, C.c_size_t, C.c_int, c_u32p, c_f32p]
         L.pccb200_kdtree_order.argtypes = [C.c_void_p, c_i16p, C.c_size_t, c_u32p]
         L.pccb200_normals.argtypes = [C.c_void_p, c_i16p, C.c_size_t, C.c_int, C.c_int, c_f64p]
+        L.pccb200_segment_frame.argtypes = [C.c_void_p, c_i16p, c_u8p, C.c_size_t, C.POINTER(SegParams), c_f64p, c_u8p, c_u8p,
+                                            C.POINTER(C.c_void_p)]
+        L.pccb200_patches_count.argtypes = [C.c_void_p]
+        L.pccb200_patches_depth_elems.restype = C.c_size_t
+        L.pccb200_patches_depth_elems.argtypes = [C.c_void_p]
+        L.pccb200_patches_occ_elems.restype = C.c_size_t
+        L.pccb200_patches_occ_elems.argtypes = [C.c_void_p]
+        L.pccb200_patches_get.argtypes = [C.c_void_p, C.c_void_p, c_i16p, c_u8p]
+        L.pccb200_patches_free.argtypes = [C.c_void_p]
         self.ctx = C.c_void_p()
         rc = L.pccb200_create(device, C.byref(self.ctx))
         if rc != 0:
@@ -348,3 +357,23 @@ class Product:
         out = np.zeros((len(xyz), 3), np.float64)
         self._check(self.lib.pccb200_normals(self.ctx, ptr(xyz, c_i16p), len(xyz), k, 1 if orient else 0, ptr(out, c_f64p)))
         return out
+
+    def segment_frame(self, xyz, rgb, params):
+        """returns dict(normals, partition0, partition1, patches: PatchSet) like Reference.segment_frame"""
+        xyz = _xyz(xyz)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        n = len(xyz)
+        normals = np.zeros((n, 3), np.float64)
+        p0 = np.zeros(n, np.uint8)
+        p1 = np.zeros(n, np.uint8)
+        h = C.c_void_p()
+        self._check(self.lib.pccb200_segment_frame(self.ctx, ptr(xyz, c_i16p), ptr(rgb, c_u8p), n, C.byref(params),
+                                                   ptr(normals, c_f64p), ptr(p0, c_u8p), ptr(p1, c_u8p), C.byref(h)))
+        L = self.lib
+        cnt = L.pccb200_patches_count(h)
+        patches = np.zeros(cnt, dtype=PATCH_DTYPE)
+        depth = np.zeros(L.pccb200_patches_depth_elems(h), np.int16)
+        occ = np.zeros(L.pccb200_patches_occ_elems(h), np.uint8)
+        self._check(L.pccb200_patches_get(h, patches.ctypes.data_as(C.c_void_p), ptr(depth, c_i16p), ptr(occ, c_u8p)))
+        L.pccb200_patches_free(h)
+        return dict(normals=normals, partition0=p0, partition1=p1, patches=PatchSet(patches, depth, occ))
