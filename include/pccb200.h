@@ -85,6 +85,11 @@ void        pccb200_destroy( pccb200_ctx* ctx );
 const char* pccb200_last_error( const pccb200_ctx* ctx );
 const char* pccb200_version( void );
 
+/* Per-stage device timing (CUDA events on the launching stream). While enabled, every entry point appends one
+ * (name, milliseconds) record per stage; read returns and clears them. names: capacity x 32 chars. */
+int pccb200_profile_enable( pccb200_ctx* ctx, int on );
+int pccb200_profile_read( pccb200_ctx* ctx, char* names, float* ms, int capacity, int* count );
+
 /* ---- stage-level entry points -------------------------------------------------------------------------
  * Each replaces one public reference class used on its own by the tools (PccAppNormalGenerator uses PCCKdTree +
  * PCCNormalsGenerator3 directly) and is what the parity tests drive. Host buffers in, host buffers out. */
@@ -102,6 +107,10 @@ int pccb200_kdtree_order( pccb200_ctx* ctx, const int16_t* xyz, size_t n, uint32
  * PCCPatchSegmenter3::compute passes (PCCPatchSegmenter.cpp:88-107): k-NN PCA normals (view point = origin),
  * orientation 0 = none, 1 = spanning tree. normals: n x 3 doubles. */
 int pccb200_normals( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int k, int orientation, double* normals );
+
+/* PCCEncoder::calculateWeightNormal (PccLibEncoder/source/PCCEncoder.cpp:3569-3626), enhancedPP on: axis weights
+ * from the projected areas of frame 0 of the GOF. bits = geometry3dCoordinatesBitdepth + 1, min_weight = minWeightEPP. */
+int pccb200_weight_normal( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int bits, double min_weight, double w[3] );
 
 /* PCCPatchSegmenter3::compute (PccLibEncoder/source/PCCPatchSegmenter.cpp:53-150), CTC path: k-d tree, normals +
  * orientation, initial segmentation, grid-based refinement, patch segmentation (a1..a11 of SURVEY.md §8a) for ONE

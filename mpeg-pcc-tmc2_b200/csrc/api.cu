@@ -11,6 +11,7 @@ struct pccb200_ctx {
   int              device = 0;
   cudaStream_t     stream = nullptr;
   std::string      lastError;
+  Profiler         prof;
   // scratch for the stage-level entry points
   KdTree           tree;
   DevBuf<int16_t>  xyzRaw;
@@ -19,6 +20,8 @@ struct pccb200_ctx {
   DevBuf<float>    nbrDist;
   DevBuf<double>   normals;
   DevBuf<uint8_t>  rgbRaw, partition;
+  DevBuf<uint32_t> faces;
+  DevBuf<unsigned> faceCounts;
   DevBuf<uchar4>   rgb4;
   OrientScratch    orient;
   RefineScratch    refine;
@@ -95,6 +98,27 @@ void pccb200_destroy( pccb200_ctx* ctx ) {
   delete ctx;
 }
 
+int pccb200_profile_enable( pccb200_ctx* ctx, int on ) {
+  if ( !ctx ) return PCCB200_ERR_BAD_ARG;
+  ctx->prof.enabled = on != 0;
+  ctx->prof.results.clear();
+  return PCCB200_OK;
+}
+
+int pccb200_profile_read( pccb200_ctx* ctx, char* names, float* ms, int capacity, int* count ) {
+  if ( !ctx || !count ) return PCCB200_ERR_BAD_ARG;
+  const int n = int( ctx->prof.results.size() );
+  *count      = n;
+  if ( names && ms ) {
+    for ( int i = 0; i < n && i < capacity; ++i ) {
+      snprintf( names + 32 * i, 32, "%s", ctx->prof.results[i].first );
+      ms[i] = ctx->prof.results[i].second;
+    }
+    ctx->prof.results.clear();
+  }
+  return PCCB200_OK;
+}
+
 const char* pccb200_last_error( const pccb200_ctx* ctx ) { return ctx ? ctx->lastError.c_str() : "null context"; }
 
 int pccb200_knn( pccb200_ctx* ctx, const int16_t* xyz, size_t n, const int16_t* q, size_t nq, int k, uint32_t* idx, float* dist2 ) {
@@ -153,6 +177,34 @@ int pccb200_normals( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int k, int 
   } );
 }
 
+int pccb200_weight_normal( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int bits, double minWeight, double w[3] ) {
+  return guarded( ctx, [&]() -> int {
+    if ( !xyz || !w || bits < 1 || bits > 12 ) return PCCB200_ERR_BAD_ARG;
+    uploadXyz( ctx, xyz, n, ctx->xyz4 );
+    const size_t words = ( size_t( 1 ) << ( 2 * bits ) ) / 32;
+    ctx->faces.reserve( 3 * words + 1 ), ctx->faceCounts.reserve( 4 );
+    projectedAreas( ctx->xyz4, n, bits, ctx->faces, ctx->faceCounts, ctx->stream );
+    unsigned cnt[3];
+    PCC_CUDA( cudaMemcpyAsync( cnt, ctx->faceCounts, sizeof( cnt ), cudaMemcpyDeviceToHost, ctx->stream ) );
+    PCC_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    // three numbers on the host: order the planes by area (stable, ascending) and derive the weights
+    int order[3] = { 0, 1, 2 };
+    for ( int a = 1; a < 3; ++a )
+      for ( int b = a; b > 0 && cnt[order[b]] < cnt[order[b - 1]]; --b ) std::swap( order[b], order[b - 1] );
+    const double c0 = double( cnt[order[0]] ), c1 = double( cnt[order[1]] ), c2 = double( cnt[order[2]] );
+    double       ax[3];
+    if ( c0 / c2 >= minWeight ) {
+      ax[order[0]] = c0 / c2, ax[order[1]] = c1 / c2, ax[order[2]] = 1.0;
+    } else {
+      const double tb = c1 / c2, ta = c0 / c2;
+      ax[order[0]] = minWeight, ax[order[2]] = 1.0;
+      ax[order[1]] = minWeight + ( tb - ta ) / ( 1.0 - ta ) * ( 1 - minWeight );
+    }
+    w[0] = ax[0], w[1] = ax[1], w[2] = ax[2];
+    return PCCB200_OK;
+  } );
+}
+
 int pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* rgb, size_t n, const pccb200_seg_params* prm,
                            double* normals, uint8_t* part0, uint8_t* part1, pccb200_patchlist** out ) {
   return guarded( ctx, [&]() -> int {
@@ -168,27 +220,57 @@ int pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* 
     }
     cudaStream_t s = ctx->stream;
     const int    k = 16;
-    uploadXyz( ctx, xyz, n, ctx->xyz4 );
-    ctx->rgbRaw.reserve( 3 * n ), ctx->rgb4.reserve( n ), ctx->partition.reserve( n );
-    PCC_CUDA( cudaMemcpyAsync( ctx->rgbRaw, rgb, 3 * n, cudaMemcpyHostToDevice, s ) );
-    packRgb( ctx->rgbRaw, n, ctx->rgb4, s );
-    kdBuild( ctx->tree, ctx->xyz4, n, s );
+    Profiler*    pf = &ctx->prof;
+    {
+      ProfScope t( pf, "h2d", s );
+      uploadXyz( ctx, xyz, n, ctx->xyz4 );
+      ctx->rgbRaw.reserve( 3 * n ), ctx->rgb4.reserve( n ), ctx->partition.reserve( n );
+      PCC_CUDA( cudaMemcpyAsync( ctx->rgbRaw, rgb, 3 * n, cudaMemcpyHostToDevice, s ) );
+      packRgb( ctx->rgbRaw, n, ctx->rgb4, s );
+    }
+    {
+      ProfScope t( pf, "kdtree_build", s );
+      kdBuild( ctx->tree, ctx->xyz4, n, s );
+    }
     ctx->nbr.reserve( n * k + 1 ), ctx->normals.reserve( 3 * n );
-    kdKnn( ctx->tree, ctx->xyz4, n, ctx->tree.vind, k, ctx->nbr, nullptr, s );
-    computeNormals( ctx->xyz4, ctx->nbr, k, n, ctx->normals, s );
-    if ( prm->normal_orientation == 1 ) orientNormals( ctx->orient, ctx->xyz4, ctx->nbr, k, n, ctx->normals, s );
+    {
+      ProfScope t( pf, "knn16", s );
+      kdKnn( ctx->tree, ctx->xyz4, n, ctx->tree.vind, k, ctx->nbr, nullptr, s );
+    }
+    {
+      ProfScope t( pf, "normals", s );
+      computeNormals( ctx->xyz4, ctx->nbr, k, n, ctx->normals, s );
+    }
+    if ( prm->normal_orientation == 1 ) {
+      ProfScope t( pf, "orient", s );
+      ctx->orient.prof = pf;
+      orientNormals( ctx->orient, ctx->xyz4, ctx->nbr, k, n, ctx->normals, s );
+    }
     if ( normals ) PCC_CUDA( cudaMemcpyAsync( normals, ctx->normals, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, s ) );
-    initialSegmentation( ctx->normals, n, prm->weight_normal, ctx->partition, s );
+    {
+      ProfScope t( pf, "initial_seg", s );
+      initialSegmentation( ctx->normals, n, prm->weight_normal, ctx->partition, s );
+    }
     if ( part0 ) PCC_CUDA( cudaMemcpyAsync( part0, ctx->partition, n, cudaMemcpyDeviceToHost, s ) );
-    refineSegmentation( ctx->refine, ctx->xyz4, ctx->normals, n, *prm, ctx->partition, s );
+    {
+      ProfScope t( pf, "refine", s );
+      refineSegmentation( ctx->refine, ctx->xyz4, ctx->normals, n, *prm, ctx->partition, s );
+    }
     if ( part1 ) PCC_CUDA( cudaMemcpyAsync( part1, ctx->partition, n, cudaMemcpyDeviceToHost, s ) );
     PatchResult res;
-    segmentPatches( ctx->patch, res, ctx->xyz4, ctx->rgb4, ctx->nbr, k, ctx->partition, n, *prm, s );
-    pl->patches = res.patches;
-    pl->depth.resize( res.depthElems ), pl->occ.resize( res.occElems );
-    if ( res.depthElems ) PCC_CUDA( cudaMemcpyAsync( pl->depth.data(), res.depth, res.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, s ) );
-    if ( res.occElems ) PCC_CUDA( cudaMemcpyAsync( pl->occ.data(), res.occ, res.occElems, cudaMemcpyDeviceToHost, s ) );
+    {
+      ProfScope t( pf, "patches", s );
+      segmentPatches( ctx->patch, res, ctx->xyz4, ctx->rgb4, ctx->nbr, k, ctx->partition, n, *prm, s );
+    }
+    {
+      ProfScope t( pf, "d2h", s );
+      pl->patches = res.patches;
+      pl->depth.resize( res.depthElems ), pl->occ.resize( res.occElems );
+      if ( res.depthElems ) PCC_CUDA( cudaMemcpyAsync( pl->depth.data(), res.depth, res.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, s ) );
+      if ( res.occElems ) PCC_CUDA( cudaMemcpyAsync( pl->occ.data(), res.occ, res.occElems, cudaMemcpyDeviceToHost, s ) );
+    }
     PCC_CUDA( cudaStreamSynchronize( s ) );
+    ctx->prof.collect( s );
     *out = pl;
     return PCCB200_OK;
   } );

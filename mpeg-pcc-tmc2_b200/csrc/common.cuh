@@ -87,7 +87,57 @@ struct PinBuf {
 size_t scanTmpElems( size_t n );
 void   exclusiveScanU32( const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp, cudaStream_t s );
 
-// Kernel timing record (filled when profiling is enabled on the ctx)
-struct StageTimer;
+// Stage / kernel timing with CUDA events on the launching stream (enabled per context; see pccb200_profile_*).
+struct Profiler {
+  struct Span {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  bool              enabled = false;
+  std::vector<Span> spans;
+  std::vector<std::pair<const char*, float>> results;  // filled by collect()
+  void begin( const char* name, cudaStream_t s ) {
+    if ( !enabled ) return;
+    Span sp{ name, nullptr, nullptr };
+    cudaEventCreate( &sp.a ), cudaEventCreate( &sp.b );
+    cudaEventRecord( sp.a, s );
+    spans.push_back( sp );
+  }
+  void end( cudaStream_t s ) {  // closes the most recent open span
+    if ( !enabled ) return;
+    // spans are strictly nested/sequential in this code base: record on the last span not yet closed
+    for ( size_t i = spans.size(); i-- > 0; )
+      if ( !closed[i] ) {
+        cudaEventRecord( spans[i].b, s );
+        closed[i] = true;
+        return;
+      }
+  }
+  std::vector<bool> closed;
+  void              collect( cudaStream_t s ) {
+    if ( !enabled ) return;
+    cudaStreamSynchronize( s );
+    for ( size_t i = 0; i < spans.size(); ++i ) {
+      float ms = 0;
+      if ( closed[i] ) cudaEventElapsedTime( &ms, spans[i].a, spans[i].b );
+      results.emplace_back( spans[i].name, ms );
+      cudaEventDestroy( spans[i].a ), cudaEventDestroy( spans[i].b );
+    }
+    spans.clear(), closed.clear();
+  }
+};
+struct ProfScope {
+  Profiler*    p;
+  cudaStream_t s;
+  ProfScope( Profiler* prof, const char* name, cudaStream_t st ) : p( prof ), s( st ) {
+    if ( p && p->enabled ) {
+      p->begin( name, s );
+      p->closed.push_back( false );
+    }
+  }
+  ~ProfScope() {
+    if ( p && p->enabled ) p->end( s );
+  }
+};
 
 }  // namespace pccb200

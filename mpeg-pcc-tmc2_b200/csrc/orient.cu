@@ -304,8 +304,11 @@ void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, i
   const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 ) * 8;
   if ( smemBytes > 200 * 1024 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   PCC_CUDA( cudaFuncSetAttribute( kWalk, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smemBytes ) ) );
-  kWalk<<<1, 32, smemBytes, s>>>( a );
-  PCC_LAUNCH_CHECK();
+  {
+    ProfScope t( sc.prof, "orient_walk", s );
+    kWalk<<<1, 32, smemBytes, s>>>( a );
+    PCC_LAUNCH_CHECK();
+  }
   kApplyFlip<<<divUp( n, 256 ), 256, 0, s>>>( normals, sc.flip, pts, int( n ), sc.counter );
   kNegateIfMajority<<<divUp( 3 * n, 256 ), 256, 0, s>>>( normals, int( n ), sc.counter );
   PCC_LAUNCH_CHECK();

@@ -16,6 +16,7 @@ struct OrientScratch {
   DevBuf<uint2>    byRank;
   DevBuf<uint8_t>  flip, cubTmp;
   DevBuf<unsigned> counter;
+  Profiler*        prof = nullptr;
 };
 void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, size_t n, double* normals, cudaStream_t s );
 
@@ -58,6 +59,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
                      const uint8_t* partition, size_t n, const pccb200_seg_params& prm, cudaStream_t s );
 
 // util.cu
+void projectedAreas( const short4* pts, size_t n, int bits, uint32_t* faces, unsigned* counts, cudaStream_t s );
 void gatherU8( const uint8_t* src, const uint32_t* idx, size_t n, uint8_t* dst, cudaStream_t s );
 void packXyz( const int16_t* xyz3, size_t n, short4* out, cudaStream_t s );  // device int16 AoS (n x 3) -> short4
 

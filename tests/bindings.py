@@ -323,6 +323,9 @@ class Product:
         L.pccb200_patches_occ_elems.argtypes = [C.c_void_p]
         L.pccb200_patches_get.argtypes = [C.c_void_p, C.c_void_p, c_i16p, c_u8p]
         L.pccb200_patches_free.argtypes = [C.c_void_p]
+        L.pccb200_weight_normal.argtypes = [C.c_void_p, c_i16p, C.c_size_t, C.c_int, C.c_double, c_f64p]
+        L.pccb200_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.pccb200_profile_read.argtypes = [C.c_void_p, C.c_char_p, c_f32p, C.c_int, C.POINTER(C.c_int)]
         self.ctx = C.c_void_p()
         rc = L.pccb200_create(device, C.byref(self.ctx))
         if rc != 0:
@@ -377,3 +380,24 @@ class Product:
         self._check(L.pccb200_patches_get(h, patches.ctypes.data_as(C.c_void_p), ptr(depth, c_i16p), ptr(occ, c_u8p)))
         L.pccb200_patches_free(h)
         return dict(normals=normals, partition0=p0, partition1=p1, patches=PatchSet(patches, depth, occ))
+
+    def profile(self, on=True):
+        self._check(self.lib.pccb200_profile_enable(self.ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """[(stage name, device milliseconds)] recorded since the last read"""
+        cap = 256
+        names = C.create_string_buffer(32 * cap)
+        ms = np.zeros(cap, np.float32)
+        cnt = C.c_int(0)
+        self._check(self.lib.pccb200_profile_read(self.ctx, names, ptr(ms, c_f32p), cap, C.byref(cnt)))
+        out = []
+        for i in range(min(cnt.value, cap)):
+            out.append((names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), float(ms[i])))
+        return out
+
+    def weight_normal(self, xyz, bits, min_w=0.6):
+        xyz = _xyz(xyz)
+        w = np.zeros(3, np.float64)
+        self._check(self.lib.pccb200_weight_normal(self.ctx, ptr(xyz, c_i16p), len(xyz), bits, min_w, ptr(w, c_f64p)))
+        return w

@@ -53,3 +53,9 @@ def test_segment_frame(name, oracle, product):
     bad = int((got["partition1"] != want["partition1"]).sum())
     assert bad == 0, "refined segmentation differs at %d points" % bad
     compare_patches(got["patches"], want["patches"])
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_weight_normal(name, oracle, product):
+    xyz = SHAPES[name]()[0]
+    assert np.array_equal(product.weight_normal(xyz, 11), oracle.weight_normal(xyz, 11))
