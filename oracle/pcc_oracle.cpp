@@ -845,4 +845,500 @@ void* pcco_segment_frame( const int16_t* xyz, const uint8_t* rgb, size_t n, cons
   return pcco_segment_patches( xyz, rgb, n, nbr.data(), p->max_nn_count_patch_seg, part.data(), p );
 }
 
+
+// ======================================================================================================
+// a13–a26. Packing, occupancy / geometry / attribute image formation, reconstruction, colour transfer, padding
+// for one GOF (CTC all-intra path), in the order PCCEncoder::encode runs them (L/PccLibEncoder/source/PCCEncoder.cpp
+// :103-424) with the video codec treated as lossless (decoded == source).
+// ======================================================================================================
+namespace {
+
+struct OFrame {
+  OPatchList            pl;  // packed order
+  size_t                width = 0, height = 0;
+  std::vector<uint8_t>  occupancy, omVideo, recRgb;
+  std::vector<uint32_t> blockToPatch, pointToPixel, recPartition;
+  std::vector<uint16_t> geo[2], recBoundary, attrRaw[2], attr[2];
+  std::vector<int16_t>  recXyz;
+};
+struct OGof {
+  std::vector<OFrame> frames;
+};
+
+enum { OR_DEFAULT = 0, OR_SWAP = 1 };  // PATCH_ORIENTATION_DEFAULT / _SWAP (PCCBitstreamCommon.h:112-122)  // PCCPatchOrientation values used by the 2-orientation flexible packer
+
+// PCCPatch::patchBlock2CanvasBlock / patch2Canvas for the two orientations in use (L/PccLibCommon/source/PCCPatch.cpp:192-308)
+inline void blockToCanvas( const pccb200_patch& m, int ub, int vb, int& x, int& y ) {
+  if ( m.orientation == OR_DEFAULT ) x = ub + m.u0, y = vb + m.v0;
+  else x = vb + m.u0, y = ub + m.v0;
+}
+inline void pixelToCanvas( const pccb200_patch& m, int occRes, int u, int v, int& x, int& y ) {
+  if ( m.orientation == OR_DEFAULT ) x = u + m.u0 * occRes, y = v + m.v0 * occRes;
+  else x = v + m.u0 * occRes, y = u + m.v0 * occRes;
+}
+
+// PCCPatch::gt (PCCPatch.cpp:349-371): larger max dimension first, then larger min dimension, then lower index
+bool patchBefore( const OPatch& a, const OPatch& b ) {
+  const int amax = std::max( a.m.size_u0, a.m.size_v0 ), amin = std::min( a.m.size_u0, a.m.size_v0 );
+  const int bmax = std::max( b.m.size_u0, b.m.size_v0 ), bmin = std::min( b.m.size_u0, b.m.size_v0 );
+  return amax != bmax ? amax > bmax : ( amin != bmin ? amin > bmin : a.m.index < b.m.index );
+}
+
+// PCCEncoder::packFlexible (PCCEncoder.cpp:2306-2449), packingStrategy 1, two orientations, safeguard 0, lowDelay off
+void packFrame( OFrame& F, int occRes, int presetWidth, int numTilesHor, double tileRatio ) {
+  auto& P  = F.pl.patches;
+  F.width  = presetWidth;
+  if ( P.empty() ) return;  // height stays at its preset
+  std::sort( P.begin(), P.end(), patchBefore );  // gt() is a strict total order: any sort gives this result
+  int sizeU = presetWidth / occRes, sizeV = std::max( P[0].m.size_v0, P[0].m.size_u0 );
+  for ( auto& p : P ) sizeU = std::max( sizeU, p.m.size_u0 + 1 );
+  const int tileW = sizeU / numTilesHor, tileH = int( tileW * tileRatio );
+  sizeV           = sizeV >= tileH ? sizeV : tileH;
+  size_t height   = size_t( sizeV ) * occRes;
+  std::vector<uint8_t> canvas( size_t( sizeU ) * sizeV, 0 );
+  for ( auto& p : P ) {
+    pccb200_patch& m = p.m;
+    bool           found = false;
+    while ( !found ) {
+      for ( int v = 0; v < sizeV && !found; ++v )
+        for ( int u = 0; u < sizeU && !found; ++u ) {
+          m.u0 = u, m.v0 = v;
+          for ( int o = 0; o < 2 && !found; ++o ) {
+            m.orientation = ( m.size_u0 > m.size_v0 ) ? ( o == 0 ? OR_SWAP : OR_DEFAULT ) : ( o == 0 ? OR_DEFAULT : OR_SWAP );
+            bool fits     = true;  // every block of the bounding box must lie on the canvas and be free
+            for ( int vb = 0; vb < m.size_v0 && fits; ++vb )
+              for ( int ub = 0; ub < m.size_u0 && fits; ++ub ) {
+                int x, y;
+                blockToCanvas( m, ub, vb, x, y );
+                if ( x >= sizeU || y >= sizeV || canvas[size_t( y ) * sizeU + x] ) fits = false;
+              }
+            found = fits;
+          }
+        }
+      if ( !found ) {
+        sizeV *= 2;
+        canvas.resize( size_t( sizeU ) * sizeV, 0 );
+      }
+    }
+    for ( int vb = 0; vb < m.size_v0; ++vb )  // only occupied blocks are taken
+      for ( int ub = 0; ub < m.size_u0; ++ub ) {
+        int x, y;
+        blockToCanvas( m, ub, vb, x, y );
+        canvas[size_t( y ) * sizeU + x] |= p.occ[size_t( vb ) * m.size_u0 + ub];
+      }
+    const int rows = m.orientation == OR_DEFAULT ? m.size_v0 : m.size_u0;
+    height         = std::max( height, size_t( m.v0 + rows ) * occRes );
+  }
+  F.height = height;
+}
+
+// weighted mean used by the push-pull filter (PCCEncoder.cpp:6357-6369)
+inline int mean4w( int p1, int w1, int p2, int w2, int p3, int w3, int p4, int w4 ) {
+  return ( p1 * w1 + p2 * w2 + p3 * w3 + p4 * w4 ) / ( w1 + w2 + w3 + w4 );
+}
+
+struct Img3 {
+  size_t                w = 0, h = 0;
+  std::vector<uint16_t> c[3];
+  void                  alloc( size_t W, size_t H ) {
+    w = W, h = H;
+    for ( auto& ch : c ) ch.assign( W * H, 0 );
+  }
+};
+
+// PCCEncoder::pushPullMip (PCCEncoder.cpp:6372-6441)
+void pullLevel( const Img3& img, const std::vector<uint8_t>& occ, Img3& mip, std::vector<uint8_t>& mipOcc ) {
+  const size_t W = img.w, H = img.h, nw = ( W + 1 ) >> 1, nh = ( H + 1 ) >> 1;
+  mip.alloc( nw, nh );
+  mipOcc.assign( nw * nh, 0 );
+  for ( size_t y = 0; y < nh; ++y )
+    for ( size_t x = 0; x < nw; ++x ) {
+      const size_t X = x << 1, Y = y << 1;
+      const bool   in2 = X + 1 < W, in3 = Y + 1 < H;
+      const int    w1 = occ[X + W * Y] ? 255 : 0, w2 = ( in2 && occ[X + 1 + W * Y] ) ? 255 : 0,
+                w3 = ( in3 && occ[X + W * ( Y + 1 )] ) ? 255 : 0, w4 = ( in2 && in3 && occ[X + 1 + W * ( Y + 1 )] ) ? 255 : 0;
+      if ( w1 + w2 + w3 + w4 == 0 ) continue;
+      for ( int ch = 0; ch < 3; ++ch ) {
+        const auto& s  = img.c[ch];
+        const int   v1 = uint8_t( s[X + W * Y] ), v2 = in2 ? uint8_t( s[X + 1 + W * Y] ) : 0, v3 = in3 ? uint8_t( s[X + W * ( Y + 1 )] ) : 0,
+                  v4 = ( in2 && in3 ) ? uint8_t( s[X + 1 + W * ( Y + 1 )] ) : 0;
+        mip.c[ch][x + nw * y] = uint16_t( mean4w( v1, w1, v2, w2, v3, w3, v4, w4 ) );
+      }
+      mipOcc[x + nw * y] = 1;
+    }
+}
+
+// PCCEncoder::pushPullFill (PCCEncoder.cpp:6444-6540)
+void pushLevel( Img3& img, const Img3& mip, const std::vector<uint8_t>& occ, int iters ) {
+  const int W = int( img.w ), H = int( img.h ), w = int( mip.w ), h = int( mip.h );
+  for ( int Y = 0; Y < H; ++Y )
+    for ( int X = 0; X < W; ++X ) {
+      if ( occ[X + size_t( W ) * Y] ) continue;
+      const int  x = X >> 1, y = Y >> 1;
+      const int  dx = ( X & 1 ) ? 1 : -1, dy = ( Y & 1 ) ? 1 : -1;  // the diagonal neighbour the sample leans towards
+      const bool okx = dx < 0 ? x > 0 : x < w - 1, oky = dy < 0 ? y > 0 : y < h - 1;
+      for ( int ch = 0; ch < 3; ++ch ) {
+        const auto& m  = mip.c[ch];
+        const int   v  = m[x + size_t( w ) * y];
+        const int   vx = okx ? m[x + dx + size_t( w ) * y] : 0, vy = oky ? m[x + size_t( w ) * ( y + dy )] : 0,
+                  vd = ( okx && oky ) ? m[x + dx + size_t( w ) * ( y + dy )] : 0;
+        img.c[ch][X + size_t( W ) * Y] = uint16_t( mean4w( v, 144, vx, okx ? 48 : 0, vy, oky ? 48 : 0, vd, ( okx && oky ) ? 16 : 0 ) );
+      }
+    }
+  Img3 tmp = img;
+  for ( int n = 0; n < iters; ++n ) {
+    for ( int y = 0; y < H; ++y )
+      for ( int x = 0; x < W; ++x ) {
+        if ( occ[x + size_t( W ) * y] ) continue;
+        const int x1 = x > 0 ? x - 1 : x, y1 = y > 0 ? y - 1 : y, x2 = x < W - 1 ? x + 1 : x, y2 = y < H - 1 ? y + 1 : y;
+        for ( int ch = 0; ch < 3; ++ch ) {
+          const auto& s   = img.c[ch];
+          auto        at  = [&]( int xx, int yy ) { return int( s[xx + size_t( W ) * yy] ); };
+          const int   val = at( x1, y1 ) + at( x2, y1 ) + at( x1, y2 ) + at( x2, y2 ) + at( x1, y ) + at( x2, y ) + at( x, y1 ) + at( x, y2 );
+          tmp.c[ch][x + size_t( W ) * y] = uint16_t( ( val + 4 ) >> 3 );
+        }
+      }
+    std::swap( img, tmp );
+  }
+}
+
+// PCCEncoder::dilateSmoothedPushPull (PCCEncoder.cpp:6542-6591)
+void pushPull( Img3& image, const std::vector<uint8_t>& occ ) {
+  std::vector<Img3>                 mips;
+  std::vector<std::vector<uint8_t>> mocc;
+  for ( ;; ) {
+    mips.emplace_back(), mocc.emplace_back();
+    const size_t l = mips.size() - 1;
+    if ( l > 0 ) pullLevel( mips[l - 1], mocc[l - 1], mips[l], mocc[l] );
+    else pullLevel( image, occ, mips[0], mocc[0] );
+    if ( mips[l].w <= 4 || mips[l].h <= 4 ) break;
+  }
+  int iters = 4;
+  for ( int i = int( mips.size() ) - 1; i >= 0; --i ) {
+    if ( i > 0 ) pushLevel( mips[i - 1], mips[i], mocc[i - 1], iters );
+    else pushLevel( image, mips[0], occ, iters );
+    iters = std::min( iters + 1, 16 );
+  }
+}
+
+}  // namespace
+
+void* pcco_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                       const pccb200_seg_params* prm, int occPrec, int stopAfter ) {
+  OGof* G = new OGof();
+  G->frames.resize( nframes );
+  const int occRes = prm->occupancy_resolution;
+  const int minW = prm->geometry_bitdepth_3d > 11 ? 2560 : 1280, minH = 1280;
+  // ---- a1..a11 per frame, then a13 packing
+  for ( int f = 0; f < nframes; ++f ) {
+    OPatchList* pl = static_cast<OPatchList*>( pcco_segment_frame( xyz[f], rgb[f], n[f], prm ) );
+    G->frames[f].pl = std::move( *pl );
+    delete pl;
+    G->frames[f].height = minH;
+    packFrame( G->frames[f], occRes, minW, 2, 1.0 );
+  }
+  // ---- a14: one canvas size for the GOF (resizeTileGeometryVideo + resizeGeometryVideo, PCCEncoder.cpp:5546-5634)
+  size_t W = minW, H = minH;
+  for ( auto& F : G->frames ) W = std::max( W, F.width ), H = std::max( H, F.height );
+  W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
+  for ( auto& F : G->frames ) F.width = W, F.height = H;
+  if ( stopAfter == 1 ) return G;
+  const size_t bw = W / occRes, bh = H / occRes, ow = W / occPrec, oh = H / occPrec;
+  for ( int f = 0; f < nframes; ++f ) {
+    OFrame& F = G->frames[f];
+    auto&   P = F.pl.patches;
+    // ---- a16 generateOccupancyMap (PCCEncoder.cpp:3768-3784)
+    F.occupancy.assign( W * H, 0 );
+    for ( auto& p : P )
+      for ( int v = 0; v < p.m.size_v; ++v )
+        for ( int u = 0; u < p.m.size_u; ++u )
+          if ( p.depth[0][size_t( v ) * p.m.size_u + u] < kInfDepth ) {
+            int x, y;
+            pixelToCanvas( p.m, occRes, u, v, x, y );
+            F.occupancy[size_t( y ) * W + x] = 1;
+          }
+    // ---- a17 generateOccupancyMapVideo (PCCEncoder.cpp:806-861): OR over each precision x precision cell
+    F.omVideo.assign( ow * oh, 0 );
+    for ( size_t y = 0; y < H; ++y )
+      for ( size_t x = 0; x < W; ++x )
+        if ( F.occupancy[y * W + x] ) F.omVideo[( y / occPrec ) * ow + x / occPrec] = 1;
+    // ---- a18 generateBlockToPatchFromOccupancyMapVideo (L/PccLibCommon/source/PCCCodec.cpp:1736-1774): last patch wins
+    F.blockToPatch.assign( bw * bh, 0 );
+    for ( size_t pi = 0; pi < P.size(); ++pi ) {
+      const pccb200_patch& m = P[pi].m;
+      for ( int vb = 0; vb < m.size_v0; ++vb )
+        for ( int ub = 0; ub < m.size_u0; ++ub ) {
+          int bx, by;
+          blockToCanvas( m, ub, vb, bx, by );
+          bool any = false;
+          for ( int v1 = 0; v1 < occRes && !any; ++v1 )
+            for ( int u1 = 0; u1 < occRes && !any; ++u1 ) {
+              int x, y;
+              pixelToCanvas( m, occRes, ub * occRes + u1, vb * occRes + v1, x, y );
+              any = F.omVideo[size_t( y / occPrec ) * ow + x / occPrec] != 0;
+            }
+          if ( any ) F.blockToPatch[size_t( by ) * bw + bx] = uint32_t( pi + 1 );
+        }
+    }
+    // ---- a19 generateIntraImage (PCCEncoder.cpp:3929-3960) + a20 dilate3DPadding (:5951-6130, geometryPadding 0)
+    for ( int map = 0; map < 2; ++map ) {
+      auto& img = F.geo[map];
+      img.assign( W * H, 0 );
+      for ( auto& p : P )
+        for ( int v = 0; v < p.m.size_v; ++v )
+          for ( int u = 0; u < p.m.size_u; ++u ) {
+            const int16_t d = p.depth[map][size_t( v ) * p.m.size_u + u];
+            if ( d < kInfDepth ) {
+              int x, y;
+              pixelToCanvas( p.m, occRes, u, v, x, y );
+              img[size_t( y ) * W + x] = uint16_t( d );
+            }
+          }
+      // fill mask: original occupancy restricted to cells active in the (lossless) occupancy video == the occupancy
+      std::vector<uint32_t> state( W * H, 0 );
+      for ( size_t i = 0; i < W * H; ++i ) state[i] = F.occupancy[i] ? 1 : 0;
+      for ( size_t vb = 0; vb < bh; ++vb )
+        for ( size_t ub = 0; ub < bw; ++ub ) {
+          const size_t x0 = ub * occRes, y0 = vb * occRes;
+          size_t       filled = 0;
+          for ( int v = 0; v < occRes; ++v )
+            for ( int u = 0; u < occRes; ++u ) filled += state[( y0 + v ) * W + x0 + u] == 1;
+          if ( filled == 0 ) {  // empty block: smear the left (else the upper) neighbour's border pixels, in raster order
+            for ( int v = 0; v < occRes; ++v )
+              for ( int u = 0; u < occRes; ++u ) {
+                const size_t x = x0 + u, y = y0 + v;
+                if ( ub > 0 ) img[y * W + x] = img[y * W + x - 1];
+                else if ( vb > 0 ) img[y * W + x] = img[( y - 1 ) * W + x];
+              }
+            continue;
+          }
+          uint32_t iteration = 1;
+          std::vector<int>      sum( size_t( occRes ) * occRes );
+          std::vector<uint32_t> cnt( size_t( occRes ) * occRes );
+          while ( filled < size_t( occRes ) * occRes ) {
+            std::fill( sum.begin(), sum.end(), 0 ), std::fill( cnt.begin(), cnt.end(), 0u );
+            static const int nb[4][2] = {{0, -1}, {-1, 0}, {1, 0}, {0, 1}};
+            for ( int v = 0; v < occRes; ++v )
+              for ( int u = 0; u < occRes; ++u ) {
+                if ( state[( y0 + v ) * W + x0 + u] != iteration ) continue;
+                for ( auto& d : nb ) {
+                  const int u3 = u + d[0], v3 = v + d[1];
+                  if ( u3 < 0 || v3 < 0 || u3 >= occRes || v3 >= occRes || state[( y0 + v3 ) * W + x0 + u3] != 0 ) continue;
+                  sum[size_t( v3 ) * occRes + u3] += img[( y0 + v ) * W + x0 + u];
+                  ++cnt[size_t( v3 ) * occRes + u3];
+                }
+              }
+            for ( int v = 0; v < occRes; ++v )
+              for ( int u = 0; u < occRes; ++u ) {
+                const uint32_t c = cnt[size_t( v ) * occRes + u];
+                if ( !c ) continue;
+                ++filled;
+                state[( y0 + v ) * W + x0 + u] = iteration + 1;
+                img[( y0 + v ) * W + x0 + u]   = uint16_t( ( sum[size_t( v ) * occRes + u] + int( c / 2 ) ) / int( c ) );
+              }
+            ++iteration;
+          }
+        }
+    }
+    // ---- a21 dilateGroupGeometryVideo (PCCEncoder.cpp:3717-3739)
+    for ( size_t y = 0; y < H; ++y )
+      for ( size_t x = 0; x < W; ++x )
+        if ( F.omVideo[( y / occPrec ) * ow + x / occPrec] == 0 ) {
+          const uint32_t avg = ( uint32_t( F.geo[0][y * W + x] ) + uint32_t( F.geo[1][y * W + x] ) + 1 ) >> 1;
+          F.geo[0][y * W + x] = F.geo[1][y * W + x] = uint16_t( avg );
+        }
+  }
+  if ( stopAfter == 2 ) return G;
+  for ( int f = 0; f < nframes; ++f ) {
+    OFrame& F = G->frames[f];
+    auto&   P = F.pl.patches;
+    // ---- a22 generatePointCloud (PCCCodec.cpp:519-980): the tile occupancy becomes the up-sampled occupancy video
+    std::vector<uint8_t> occ( W * H );
+    for ( size_t y = 0; y < H; ++y )
+      for ( size_t x = 0; x < W; ++x ) occ[y * W + x] = F.omVideo[( y / occPrec ) * ow + x / occPrec];
+    for ( size_t pi = 0; pi < P.size(); ++pi ) {
+      const pccb200_patch& m = P[pi].m;
+      for ( int vb = 0; vb < m.size_v0; ++vb )
+        for ( int ub = 0; ub < m.size_u0; ++ub ) {
+          int bx, by;
+          blockToCanvas( m, ub, vb, bx, by );
+          if ( F.blockToPatch[size_t( by ) * bw + bx] != pi + 1 ) continue;
+          for ( int v1 = 0; v1 < occRes; ++v1 )
+            for ( int u1 = 0; u1 < occRes; ++u1 ) {
+              const int u = ub * occRes + u1, v = vb * occRes + v1;
+              int       x, y;
+              pixelToCanvas( m, occRes, u, v, x, y );
+              if ( !occ[size_t( y ) * W + x] ) continue;
+              int16_t pt[2][3];
+              for ( int map = 0; map < 2; ++map ) {  // PCCPatch::generatePoint (PCCPatch.h:177-207)
+                const uint16_t depth = F.geo[map][size_t( y ) * W + x];
+                double         nc    = 0;
+                if ( m.projection_mode == 0 ) nc = double( depth ) + double( m.d1 );
+                else {
+                  const double t = double( m.d1 ) - double( depth );
+                  if ( t > 0 ) nc = t;
+                }
+                pt[map][m.normal_axis]    = int16_t( nc );
+                pt[map][m.tangent_axis]   = int16_t( double( u ) + m.u1 );
+                pt[map][m.bitangent_axis] = int16_t( double( v ) + m.v1 );
+              }
+              for ( int map = 0; map < 2; ++map ) {
+                if ( map == 1 && pt[1][0] == pt[0][0] && pt[1][1] == pt[0][1] && pt[1][2] == pt[0][2] ) continue;  // removeDuplicatePoints
+                F.recXyz.insert( F.recXyz.end(), pt[map], pt[map] + 3 );
+                F.pointToPixel.push_back( uint32_t( x ) ), F.pointToPixel.push_back( uint32_t( y ) ), F.pointToPixel.push_back( uint32_t( map ) );
+                F.recPartition.push_back( uint32_t( pi ) );
+              }
+            }
+        }
+    }
+    // identifyBoundaryPoints (PCCCodec.cpp:268-327): 3x3 then 5x5 ring of the occupancy, plus the image border
+    const size_t R = F.recPartition.size();
+    F.recBoundary.assign( R, 0 );
+    auto at = [&]( long x, long y ) { return occ[size_t( y ) * W + size_t( x )]; };
+    for ( size_t i = 0; i < R; ++i ) {
+      const long x = F.pointToPixel[3 * i], y = F.pointToPixel[3 * i + 1];
+      if ( !at( x, y ) ) continue;
+      bool b = false;
+      const bool yIn = y > 0 && y < long( H ) - 1, xIn = x > 0 && x < long( W ) - 1;
+      if ( yIn && ( !at( x, y - 1 ) || !at( x, y + 1 ) ) ) b = true;
+      if ( !b && xIn && ( !at( x + 1, y ) || !at( x - 1, y ) ) ) b = true;
+      if ( !b && yIn && x > 0 && ( !at( x - 1, y - 1 ) || !at( x - 1, y + 1 ) ) ) b = true;
+      if ( !b && yIn && x < long( W ) - 1 && ( !at( x + 1, y - 1 ) || !at( x + 1, y + 1 ) ) ) b = true;
+      if ( y == 0 || y == long( H ) - 1 || x == 0 || x == long( W ) - 1 ) b = true;
+      if ( !b ) {
+        for ( int ix = -2; ix <= 2 && !b; ++ix )
+          for ( int iy = -2; iy <= 2 && !b; ++iy )
+            if ( ( std::abs( ix ) > 1 || std::abs( iy ) > 1 ) && y + iy >= 0 && y + iy < long( H ) && x + ix >= 0 && x + ix < long( W ) &&
+                 !at( x + ix, y + iy ) )
+              b = true;
+        if ( y == 1 || y == long( H ) - 2 || x == 1 || x == long( W ) - 2 ) b = true;
+      }
+      F.recBoundary[i] = b ? 1 : 0;
+    }
+    if ( stopAfter == 3 ) continue;
+    // ---- a23 transferColors (L/PccLibCommon/source/PCCPointSet.cpp:807-1124), CTC values: 8 fwd / 1 bwd neighbours,
+    //      distance-weighted, offsets 4, all distance/colour gates disabled (1000 >= 512), search range 0, fixWeight.
+    F.recRgb.assign( 3 * R, 0 );
+    if ( R && n[f] ) {
+      Tree src, tgt;
+      src.build( xyz[f], n[f] );
+      tgt.build( F.recXyz.data(), R );
+      std::vector<uint8_t> fwd( 3 * R );
+      for ( size_t i = 0; i < R; ++i ) {
+        uint32_t id[8];
+        double   d[8];
+        KnnSet   rs( 8, id, d );
+        src.search( rs, &F.recXyz[3 * i] );
+        const uint8_t* c0 = rgb[f] + 3 * size_t( id[0] );
+        if ( d[0] < 0.0001 || rs.cnt == 1 ) {
+          for ( int k = 0; k < 3; ++k ) fwd[3 * i + k] = c0[k];
+        } else {
+          double acc[3] = {0, 0, 0}, sw = 0;
+          for ( int j = 0; j < rs.cnt; ++j ) {
+            const double wgt = 1 / ( d[j] + 4.0 );
+            for ( int k = 0; k < 3; ++k ) acc[k] += rgb[f][3 * size_t( id[j] ) + k] * wgt;
+            sw += wgt;
+          }
+          for ( int k = 0; k < 3; ++k ) {
+            const double v = std::round( acc[k] / sw );
+            fwd[3 * i + k] = uint8_t( v < 0.0 ? 0.0 : ( v > 255.0 ? 255.0 : v ) );
+          }
+        }
+      }
+      struct Vote {
+        double  dist;
+        uint8_t c[3];
+      };
+      std::vector<std::vector<Vote>> votes( R );
+      for ( size_t s = 0; s < n[f]; ++s ) {
+        uint32_t id;
+        double   d;
+        KnnSet   rs( 1, &id, &d );
+        tgt.search( rs, xyz[f] + 3 * s );
+        votes[id].push_back( Vote{d, {rgb[f][3 * s], rgb[f][3 * s + 1], rgb[f][3 * s + 2]}} );
+      }
+      for ( size_t i = 0; i < R; ++i ) {
+        auto& v = votes[i];
+        if ( v.empty() ) {
+          for ( int k = 0; k < 3; ++k ) F.recRgb[3 * i + k] = fwd[3 * i + k];
+          continue;
+        }
+        std::sort( v.begin(), v.end(), []( const Vote& a, const Vote& b ) { return a.dist < b.dist; } );
+        double c2[3] = {0, 0, 0};
+        if ( v[0].dist < 0.0001 || v.size() == 1 ) {
+          for ( int k = 0; k < 3; ++k ) c2[k] = v[0].c[k];
+        } else {
+          double sw = 0;
+          for ( auto& e : v ) {
+            const double wgt = 1 / ( std::sqrt( e.dist ) + 4.0 );
+            for ( int k = 0; k < 3; ++k ) c2[k] += ( e.c[k] * wgt );
+            sw += wgt;
+          }
+          for ( int k = 0; k < 3; ++k ) c2[k] /= sw;
+        }
+        for ( int k = 0; k < 3; ++k ) {
+          const double r = std::round( 0.0 * double( fwd[3 * i + k] ) + 1.0 * c2[k] );
+          F.recRgb[3 * i + k] = uint8_t( r < 0.0 ? 0.0 : ( r > 255.0 ? 255.0 : r ) );
+        }
+      }
+    }
+    // (a24 presmoothPointCloudColor only touches points of boundary type 2, which no point has at this stage.)
+    // ---- a25 generateAttributeVideo(tile) (PCCEncoder.cpp:6736-6819): T1 shows the D1 colour, else the D0 colour
+    Img3 T[2];
+    T[0].alloc( W, H ), T[1].alloc( W, H );
+    std::vector<uint8_t> hasD1( W * H, 0 );
+    for ( size_t i = 0; i < R; ++i ) {
+      const size_t x = F.pointToPixel[3 * i], y = F.pointToPixel[3 * i + 1], map = F.pointToPixel[3 * i + 2];
+      for ( int k = 0; k < 3; ++k ) T[map].c[k][y * W + x] = F.recRgb[3 * i + k];
+      if ( map == 0 ) {
+        if ( !hasD1[y * W + x] )
+          for ( int k = 0; k < 3; ++k ) T[1].c[k][y * W + x] = F.recRgb[3 * i + k];
+      } else {
+        hasD1[y * W + x] = 1;
+      }
+    }
+    for ( int map = 0; map < 2; ++map ) {
+      F.attrRaw[map].resize( 3 * W * H );
+      for ( int k = 0; k < 3; ++k ) std::copy( T[map].c[k].begin(), T[map].c[k].end(), F.attrRaw[map].begin() + k * W * H );
+    }
+    // ---- a26 push-pull background fill with the block-precision occupancy
+    for ( int map = 0; map < 2; ++map ) {
+      pushPull( T[map], occ );
+      F.attr[map].resize( 3 * W * H );
+      for ( int k = 0; k < 3; ++k ) std::copy( T[map].c[k].begin(), T[map].c[k].end(), F.attr[map].begin() + k * W * H );
+    }
+  }
+  return G;
+}
+
+void pcco_gof_free( void* h ) { delete static_cast<OGof*>( h ); }
+void pcco_gof_dims( void* h, int f, size_t* w, size_t* hgt, size_t* recPoints ) {
+  auto& F = static_cast<OGof*>( h )->frames[f];
+  *w = F.width, *hgt = F.height, *recPoints = F.recPartition.size();
+}
+void*  pcco_gof_patches( void* h, int f ) { return &static_cast<OGof*>( h )->frames[f].pl; }
+size_t pcco_gof_get( void* h, int f, int what, void* dst ) {
+  auto& R   = static_cast<OGof*>( h )->frames[f];
+  auto  put = [&]( const void* src, size_t bytes ) {
+    if ( dst && bytes ) std::memcpy( dst, src, bytes );
+  };
+  switch ( what ) {
+    case 1: put( R.occupancy.data(), R.occupancy.size() ); return R.occupancy.size();
+    case 2: put( R.omVideo.data(), R.omVideo.size() ); return R.omVideo.size();
+    case 3: put( R.blockToPatch.data(), R.blockToPatch.size() * 4 ); return R.blockToPatch.size();
+    case 4: put( R.geo[0].data(), R.geo[0].size() * 2 ); return R.geo[0].size();
+    case 5: put( R.geo[1].data(), R.geo[1].size() * 2 ); return R.geo[1].size();
+    case 6: put( R.recXyz.data(), R.recXyz.size() * 2 ); return R.recXyz.size();
+    case 7: put( R.pointToPixel.data(), R.pointToPixel.size() * 4 ); return R.pointToPixel.size();
+    case 8: put( R.recPartition.data(), R.recPartition.size() * 4 ); return R.recPartition.size();
+    case 9: put( R.recBoundary.data(), R.recBoundary.size() * 2 ); return R.recBoundary.size();
+    case 10: put( R.recRgb.data(), R.recRgb.size() ); return R.recRgb.size();
+    case 11: put( R.attrRaw[0].data(), R.attrRaw[0].size() * 2 ); return R.attrRaw[0].size();
+    case 12: put( R.attrRaw[1].data(), R.attrRaw[1].size() * 2 ); return R.attrRaw[1].size();
+    case 13: put( R.attr[0].data(), R.attr[0].size() * 2 ); return R.attr[0].size();
+    case 14: put( R.attr[1].data(), R.attr[1].size() * 2 ); return R.attr[1].size();
+    default: return 0;
+  }
+}
+
 }  // extern "C"

@@ -61,6 +61,15 @@ void   pcco_patches_free( void* pl );
 /* ---- whole-frame convenience: a1..a11 (PCCPatchSegmenter3::compute, PCCPatchSegmenter.cpp:53-150) ---- */
 void* pcco_segment_frame( const int16_t* xyz, const uint8_t* rgb, size_t n, const pccb200_seg_params* p );
 
+/* ---- a13–a26 for one GOF (PCCEncoder::encode :103-424 with a lossless codec); products by id, see tests/bindings.py
+ * stop_after: 0 all, 1 packing, 2 geometry images, 3 generatePointCloud */
+void*  pcco_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                        const pccb200_seg_params* p, int occupancy_precision, int stop_after );
+void   pcco_gof_free( void* h );
+void   pcco_gof_dims( void* h, int f, size_t* w, size_t* hgt, size_t* rec_points );
+void*  pcco_gof_patches( void* h, int f ); /* borrowed patch list for pcco_patches_* */
+size_t pcco_gof_get( void* h, int f, int what, void* dst );
+
 #ifdef __cplusplus
 }
 #endif

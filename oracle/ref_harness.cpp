@@ -7,6 +7,8 @@
 // Nothing here re-implements an algorithm: every function converts plain arrays to the reference's containers,
 // calls the reference's own methods and converts back.
 // (built with -fno-access-control so the harness can call the reference's private stage methods)
+// The reference's PCCEncoder.cpp, unmodified, is part of this translation unit (see oracle/Makefile).
+#include "PCCEncoder.cpp"
 #include "PCCCommon.h"
 #include "PCCHighLevelSyntax.h"
 #include "PCCBitstream.h"
@@ -30,6 +32,7 @@
 #include <cstring>
 #include <iostream>
 #include <sstream>
+#include <unistd.h>
 
 using namespace pcc;
 
@@ -298,5 +301,263 @@ void ref_patches_get( void* h, pccb200_patch* out, int16_t* depth, uint8_t* occ 
   }
 }
 void ref_patches_free( void* h ) { delete static_cast<PatchList*>( h ); }
+
+}  // extern "C"
+
+// =====================================================================================================
+// GOF-level harness: the reference's own encoder stages, in the order PCCEncoder::encode runs them
+// (PccLibEncoder/source/PCCEncoder.cpp:71-424), with the three videoEncoder.compress calls replaced by
+// identity (a lossless codec: decoded == source). Exposes every intermediate product the hot path hands over.
+// =====================================================================================================
+namespace {
+
+struct RefFrame {
+  PatchList            patches;  // packed order, with u0/v0/orientation
+  size_t               width = 0, height = 0;
+  std::vector<uint8_t> occupancy, omVideo;
+  std::vector<uint32_t> blockToPatch;
+  std::vector<uint16_t> geo[2];
+  std::vector<int16_t>  recXyz;
+  std::vector<uint32_t> pointToPixel, recPartition;
+  std::vector<uint16_t> recBoundary;
+  std::vector<uint8_t>  recRgb;
+  std::vector<uint16_t> attrRaw[2], attr[2];
+};
+struct RefGof {
+  std::vector<RefFrame> frames;
+  double                seconds[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // segment, pack, occupancy, geometry, reconstruct, attribute, padding, total
+};
+
+void setCtcParams( PCCEncoderParameters& ep, const pccb200_seg_params& p, int occupancyPrecision ) {
+  // cfg/common/ctc-common.cfg + cfg/condition/ctc-all-intra.cfg + per-sequence values carried in pccb200_seg_params
+  ep.nnNormalEstimation_                  = p.nn_normal_estimation;
+  ep.normalOrientation_                   = p.normal_orientation;
+  ep.gridBasedRefineSegmentation_         = true;
+  ep.maxNNCountRefineSegmentation_        = p.max_nn_count_refine;
+  ep.iterationCountRefineSegmentation_    = p.iteration_count_refine;
+  ep.voxelDimensionRefineSegmentation_    = p.voxel_dim_refine;
+  ep.searchRadiusRefineSegmentation_      = p.search_radius_refine;
+  ep.occupancyResolution_                 = p.occupancy_resolution;
+  ep.enablePatchSplitting_                = p.enable_patch_splitting != 0;
+  ep.maxPatchSize_                        = p.max_patch_size;
+  ep.minPointCountPerCCPatchSegmentation_ = p.min_point_count_per_cc;
+  ep.maxNNCountPatchSegmentation_         = p.max_nn_count_patch_seg;
+  ep.surfaceThickness_                    = p.surface_thickness;
+  ep.minLevel_                            = p.min_level;
+  ep.maxAllowedDist2RawPointsDetection_   = p.max_allowed_dist2_raw_detection;
+  ep.maxAllowedDist2RawPointsSelection_   = p.max_allowed_dist2_raw_selection;
+  ep.lambdaRefineSegmentation_            = p.lambda_refine;
+  ep.mapCountMinus1_                      = p.map_count_minus1;
+  ep.geometry3dCoordinatesBitdepth_       = p.geometry_bitdepth_3d - 1;
+  ep.geometryNominal2dBitdepth_           = p.geometry_bitdepth_2d;
+  ep.minimumImageWidth_                   = p.geometry_bitdepth_3d > 11 ? 2560 : 1280;
+  ep.minimumImageHeight_                  = 1280;
+  ep.occupancyPrecision_                  = occupancyPrecision;
+  ep.bestColorSearchRange_                = 0;
+  ep.numNeighborsColorTransferFwd_        = 8;
+  ep.numNeighborsColorTransferBwd_        = 1;
+  ep.useDistWeightedAverageFwd_ = ep.useDistWeightedAverageBwd_ = true;
+  ep.skipAvgIfIdenticalSourcePointPresentFwd_ = ep.skipAvgIfIdenticalSourcePointPresentBwd_ = true;
+  ep.distOffsetFwd_ = ep.distOffsetBwd_ = 4;
+  ep.maxGeometryDist2Fwd_ = ep.maxGeometryDist2Bwd_ = 1000;
+  ep.maxColorDist2Fwd_ = ep.maxColorDist2Bwd_ = 1000;
+  ep.flagGeometrySmoothing_               = true;
+  ep.gridSmoothing_                       = true;
+  ep.flagColorPreSmoothing_               = true;
+  ep.enablePointCloudPartitioning_        = false;
+  ep.enhancedOccupancyMapCode_            = false;
+  ep.profileReconstructionIdc_            = 1;
+  ep.constrainedPack_                     = false;
+  ep.globalPatchAllocation_               = 0;
+  ep.nbThread_                            = 1;
+  ep.groupOfFramesSize_                   = 32;
+  ep.compressedStreamPath_                = "/tmp/pccb200_ref_harness.bin";
+}
+
+template <typename T>
+void planes( const PCCImage<T, 3>& img, std::vector<uint16_t>& out ) {
+  const size_t n = img.getWidth() * img.getHeight();
+  out.resize( 3 * n );
+  for ( int c = 0; c < 3; ++c )
+    for ( size_t i = 0; i < n; ++i ) out[c * n + i] = uint16_t( img.getChannel( c )[i] );
+}
+
+}  // namespace
+
+extern "C" {
+
+// frames: nframes clouds (xyz[f]: n[f] x 3 int16, rgb[f]: n[f] x 3 uint8). stopAfter: 0 = everything,
+// 1 = after packing, 2 = after geometry images, 3 = after generatePointCloud (saves time in focused tests).
+void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                      const pccb200_seg_params* p, int occupancyPrecision, int stopAfter ) {
+  Quiet  quiet;
+  FILE*  devnull  = fopen( "/dev/null", "w" );
+  int    savedOut = dup( 1 );
+  fflush( stdout );
+  dup2( fileno( devnull ), 1 );  // the reference also chats through printf
+  RefGof* G = new RefGof();
+  G->frames.resize( nframes );
+  using clk = std::chrono::steady_clock;
+  auto secs = []( clk::time_point a ) { return std::chrono::duration<double>( clk::now() - a ).count(); };
+  {
+    PCCEncoderParameters ep;
+    setCtcParams( ep, *p, occupancyPrecision );
+    ep.check();
+    PCCGroupOfFrames sources, reconstructs;
+    sources.setFrameCount( nframes );
+    for ( int f = 0; f < nframes; ++f ) toPointSet( xyz[f], rgb[f], n[f], sources[f] );
+    PCCLogger  logger;
+    PCCEncoder enc;
+    enc.setLogger( logger );
+    enc.setParameters( ep );
+    PCCContext context;
+    context.addV3CParameterSet( 0 );
+    context.setActiveVpsId( 0 );
+    auto tAll = clk::now();
+    // ---- PCCEncoder::encode, :80-100
+    reconstructs.setFrameCount( sources.getFrameCount() );
+    context.resizeAtlas( 1 );
+    context.setAtlasIndex( 0 );
+    context.resize( sources.getFrameCount() );
+    auto& frames = context.getFrames();
+    for ( size_t i = 0; i < frames.size(); i++ ) {
+      auto& fc = frames[i].getTitleFrameContext();
+      fc.setFrameIndex( i );
+      fc.setRawPatchEnabledFlag( false );
+      fc.setUseRawPointsSeparateVideo( false );
+      fc.setGeometry3dCoordinatesBitdepth( enc.params_.geometry3dCoordinatesBitdepth_ + 1 );
+      fc.setGeometry2dBitdepth( enc.params_.geometryNominal2dBitdepth_ );
+      fc.setMaxDepth( ( 1 << enc.params_.geometryNominal2dBitdepth_ ) - 1 );
+      fc.setLog2PatchQuantizerSizeX( enc.params_.log2QuantizerSizeX_ );
+      fc.setLog2PatchQuantizerSizeY( enc.params_.log2QuantizerSizeY_ );
+    }
+    auto t0 = clk::now();
+    enc.generateSegments( sources, context );  // :103
+    G->seconds[0] = secs( t0 );
+    enc.params_.initializeContext( context );   // :107
+    t0 = clk::now();
+    enc.placeSegments( sources, context );  // :110
+    G->seconds[1] = secs( t0 );
+    for ( int f = 0; f < nframes; ++f ) {
+      auto& tile             = context[f].getTile( 0 );
+      G->frames[f].patches.patches = tile.getPatches();
+      G->frames[f].width     = context[f].getAtlasFrameWidth();
+      G->frames[f].height    = context[f].getAtlasFrameHeight();
+    }
+    if ( stopAfter != 1 ) {
+      t0 = clk::now();
+      enc.generateOccupancyMap( context, true );         // :133
+      enc.generateOccupancyMapVideo( sources, context );  // :139  (compress skipped: lossless)
+      enc.generateBlockToPatchFromOccupancyMapVideo( context, enc.params_.occupancyResolution_, enc.params_.occupancyPrecision_ );  // :168
+      G->seconds[2] = secs( t0 );
+      for ( int f = 0; f < nframes; ++f ) {
+        auto& R   = G->frames[f];
+        auto& occ = context[f].getTitleFrameContext().getOccupancyMap();
+        R.occupancy.assign( occ.begin(), occ.end() );
+        auto& om = context.getVideoOccupancyMap().getFrame( f );
+        R.omVideo.assign( om.getChannel( 0 ).begin(), om.getChannel( 0 ).end() );
+        auto& b2p = context[f].getTile( 0 ).getBlockToPatch();
+        R.blockToPatch.assign( b2p.begin(), b2p.end() );
+      }
+      t0 = clk::now();
+      enc.generateGeometryVideo( sources, context );  // :172
+      G->seconds[3] = secs( t0 );
+      for ( int f = 0; f < nframes; ++f )
+        for ( int m = 0; m < 2; ++m ) {
+          auto& img = context.getVideoGeometryMultiple()[0].getFrame( 2 * f + m );
+          G->frames[f].geo[m].assign( img.getChannel( 0 ).begin(), img.getChannel( 0 ).end() );
+        }
+    }
+    if ( stopAfter == 0 || stopAfter == 3 ) {
+      t0 = clk::now();
+      GeneratePointCloudParameters gpc;
+      enc.setGeneratePointCloudParameters( gpc, context );  // :315
+      context.allocOneLayerData();
+      std::vector<std::vector<uint32_t>> partitions( context.size() );
+      for ( size_t f = 0; f < context.size(); f++ ) {
+        PCCPointSet3 rec;
+        enc.generatePointCloud( rec, context, f, 0, gpc, partitions[f], false );  // :328
+        reconstructs[f].appendPointSet( rec );
+      }
+      G->seconds[4] = secs( t0 );
+      for ( int f = 0; f < nframes; ++f ) {
+        auto&        R   = G->frames[f];
+        auto&        rec = reconstructs[f];
+        const size_t m   = rec.getPointCount();
+        R.recXyz.resize( 3 * m ), R.recBoundary.resize( m );
+        for ( size_t i = 0; i < m; ++i ) {
+          for ( int d = 0; d < 3; ++d ) R.recXyz[3 * i + d] = rec[i][d];
+          R.recBoundary[i] = rec.getBoundaryPointType( i );
+        }
+        auto& p2p = context[f].getTitleFrameContext().getPointToPixel();
+        R.pointToPixel.resize( 3 * p2p.size() );
+        for ( size_t i = 0; i < p2p.size(); ++i )
+          for ( int d = 0; d < 3; ++d ) R.pointToPixel[3 * i + d] = uint32_t( p2p[i][d] );
+        R.recPartition = partitions[f];
+      }
+    }
+    if ( stopAfter == 0 ) {
+      t0 = clk::now();
+      enc.generateAttributeVideo( sources, reconstructs, context, enc.params_ );  // :341
+      G->seconds[5] = secs( t0 );
+      auto& video = context.getVideoAttributesMultiple()[0];
+      for ( int f = 0; f < nframes; ++f ) {
+        auto& R = G->frames[f];
+        for ( int m = 0; m < 2; ++m ) planes( video.getFrame( 2 * f + m ), R.attrRaw[m] );
+        auto&        rec = reconstructs[f];
+        const size_t mP  = rec.getPointCount();
+        R.recRgb.resize( 3 * mP );
+        for ( size_t i = 0; i < mP; ++i )
+          for ( int d = 0; d < 3; ++d ) R.recRgb[3 * i + d] = rec.getColor( i )[d];
+      }
+      t0 = clk::now();
+      for ( int f = 0; f < nframes; ++f )
+        for ( int m = 0; m < 2; ++m ) enc.dilateSmoothedPushPull( frames[f].getTitleFrameContext(), video.getFrame( 2 * f + m ) );  // :367
+      G->seconds[6] = secs( t0 );
+      for ( int f = 0; f < nframes; ++f )
+        for ( int m = 0; m < 2; ++m ) planes( video.getFrame( 2 * f + m ), G->frames[f].attr[m] );
+    }
+    G->seconds[7] = secs( tAll );
+  }
+  fflush( stdout );
+  dup2( savedOut, 1 );
+  close( savedOut );
+  fclose( devnull );
+  return G;
+}
+
+void   ref_gof_free( void* h ) { delete static_cast<RefGof*>( h ); }
+void   ref_gof_seconds( void* h, double* out ) { std::memcpy( out, static_cast<RefGof*>( h )->seconds, 8 * sizeof( double ) ); }
+void   ref_gof_dims( void* h, int f, size_t* w, size_t* hgt, size_t* recPoints ) {
+  auto& R = static_cast<RefGof*>( h )->frames[f];
+  *w = R.width, *hgt = R.height, *recPoints = R.recXyz.size() / 3;
+}
+void* ref_gof_patches( void* h, int f ) {  // borrowed view usable with ref_patches_* (do NOT free)
+  return &static_cast<RefGof*>( h )->frames[f].patches;
+}
+// what: see tests/bindings.py GOF_* ; returns the element count, copies when dst != NULL
+size_t ref_gof_get( void* h, int f, int what, void* dst ) {
+  auto&  R = static_cast<RefGof*>( h )->frames[f];
+  auto   put = [&]( const void* src, size_t bytes ) {
+    if ( dst && bytes ) std::memcpy( dst, src, bytes );
+  };
+  switch ( what ) {
+    case 1: put( R.occupancy.data(), R.occupancy.size() ); return R.occupancy.size();
+    case 2: put( R.omVideo.data(), R.omVideo.size() ); return R.omVideo.size();
+    case 3: put( R.blockToPatch.data(), R.blockToPatch.size() * 4 ); return R.blockToPatch.size();
+    case 4: put( R.geo[0].data(), R.geo[0].size() * 2 ); return R.geo[0].size();
+    case 5: put( R.geo[1].data(), R.geo[1].size() * 2 ); return R.geo[1].size();
+    case 6: put( R.recXyz.data(), R.recXyz.size() * 2 ); return R.recXyz.size();
+    case 7: put( R.pointToPixel.data(), R.pointToPixel.size() * 4 ); return R.pointToPixel.size();
+    case 8: put( R.recPartition.data(), R.recPartition.size() * 4 ); return R.recPartition.size();
+    case 9: put( R.recBoundary.data(), R.recBoundary.size() * 2 ); return R.recBoundary.size();
+    case 10: put( R.recRgb.data(), R.recRgb.size() ); return R.recRgb.size();
+    case 11: put( R.attrRaw[0].data(), R.attrRaw[0].size() * 2 ); return R.attrRaw[0].size();
+    case 12: put( R.attrRaw[1].data(), R.attrRaw[1].size() * 2 ); return R.attrRaw[1].size();
+    case 13: put( R.attr[0].data(), R.attr[0].size() * 2 ); return R.attr[0].size();
+    case 14: put( R.attr[1].data(), R.attr[1].size() * 2 ); return R.attr[1].size();
+    default: return 0;
+  }
+}
 
 }  // extern "C"

@@ -401,3 +401,146 @@ class Product:
         w = np.zeros(3, np.float64)
         self._check(self.lib.pccb200_weight_normal(self.ctx, ptr(xyz, c_i16p), len(xyz), bits, min_w, ptr(w, c_f64p)))
         return w
+
+
+# ---------------------------------------------------------------------------------------- GOF-level products
+GOF_OCCUPANCY, GOF_OM_VIDEO, GOF_BLOCK_TO_PATCH, GOF_GEO0, GOF_GEO1, GOF_REC_XYZ, GOF_POINT_TO_PIXEL = 1, 2, 3, 4, 5, 6, 7
+GOF_REC_PARTITION, GOF_REC_BOUNDARY, GOF_REC_RGB, GOF_ATTR0_RAW, GOF_ATTR1_RAW, GOF_ATTR0, GOF_ATTR1 = 8, 9, 10, 11, 12, 13, 14
+GOF_DTYPES = {1: np.uint8, 2: np.uint8, 3: np.uint32, 4: np.uint16, 5: np.uint16, 6: np.int16, 7: np.uint32, 8: np.uint32,
+              9: np.uint16, 10: np.uint8, 11: np.uint16, 12: np.uint16, 13: np.uint16, 14: np.uint16}
+
+
+class GofFrame:
+    """products of one frame: dict-like access by GOF_* id, plus packed patches and canvas size"""
+
+    def __init__(self):
+        self.patches, self.width, self.height, self.data = None, 0, 0, {}
+
+    def __getitem__(self, what):
+        return self.data[what]
+
+
+def _frames_args(frames):
+    n = len(frames)
+    xs = [np.ascontiguousarray(f[0], np.int16) for f in frames]
+    cs = [np.ascontiguousarray(f[1], np.uint8) for f in frames]
+    xp = (c_i16p * n)(*[ptr(x, c_i16p) for x in xs])
+    cp = (c_u8p * n)(*[ptr(c, c_u8p) for c in cs])
+    ns = (C.c_size_t * n)(*[len(x) for x in xs])
+    return n, xs, cs, xp, cp, ns
+
+
+def _collect_patches_borrowed(lib, prefix, h):
+    n = getattr(lib, prefix + "patches_count")(h)
+    patches = np.zeros(n, dtype=PATCH_DTYPE)
+    depth = np.zeros(getattr(lib, prefix + "patches_depth_elems")(h), dtype=np.int16)
+    occ = np.zeros(getattr(lib, prefix + "patches_occ_elems")(h), dtype=np.uint8)
+    getattr(lib, prefix + "patches_get")(h, patches.ctypes.data_as(C.c_void_p), ptr(depth, c_i16p), ptr(occ, c_u8p))
+    return PatchSet(patches, depth, occ)
+
+
+def _ref_encode_gof(self, frames, params, occupancy_precision=4, stop_after=0):
+    """runs the reference's own stages over a GOF; returns (list of GofFrame, seconds[8])"""
+    L = self.lib
+    L.ref_encode_gof.restype = C.c_void_p
+    L.ref_encode_gof.argtypes = [C.c_int, C.POINTER(c_i16p), C.POINTER(c_u8p), C.POINTER(C.c_size_t), C.POINTER(SegParams), C.c_int, C.c_int]
+    L.ref_gof_free.argtypes = [C.c_void_p]
+    L.ref_gof_seconds.argtypes = [C.c_void_p, c_f64p]
+    L.ref_gof_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.ref_gof_patches.restype = C.c_void_p
+    L.ref_gof_patches.argtypes = [C.c_void_p, C.c_int]
+    L.ref_gof_get.restype = C.c_size_t
+    L.ref_gof_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    n, xs, cs, xp, cp, ns = _frames_args(frames)
+    h = L.ref_encode_gof(n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after)
+    out = []
+    for f in range(n):
+        g = GofFrame()
+        w, hh, r = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        L.ref_gof_dims(h, f, C.byref(w), C.byref(hh), C.byref(r))
+        g.width, g.height = w.value, hh.value
+        g.patches = _collect_patches_borrowed(L, "ref_", L.ref_gof_patches(h, f))
+        for what, dt in GOF_DTYPES.items():
+            cnt = L.ref_gof_get(h, f, what, None)
+            a = np.zeros(cnt, dt)
+            if cnt:
+                L.ref_gof_get(h, f, what, a.ctypes.data_as(C.c_void_p))
+            g.data[what] = a
+        out.append(g)
+    sec = np.zeros(8)
+    L.ref_gof_seconds(h, ptr(sec, c_f64p))
+    L.ref_gof_free(h)
+    return out, sec
+
+
+Reference.encode_gof = _ref_encode_gof
+
+
+def _generic_encode_gof(lib, prefix, frames, params, occupancy_precision=4, stop_after=0):
+    g = lambda name: getattr(lib, prefix + name)
+    g("encode_gof").restype = C.c_void_p
+    g("encode_gof").argtypes = [C.c_int, C.POINTER(c_i16p), C.POINTER(c_u8p), C.POINTER(C.c_size_t), C.POINTER(SegParams), C.c_int, C.c_int]
+    g("gof_free").argtypes = [C.c_void_p]
+    g("gof_dims").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    g("gof_patches").restype = C.c_void_p
+    g("gof_patches").argtypes = [C.c_void_p, C.c_int]
+    g("gof_get").restype = C.c_size_t
+    g("gof_get").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    n, xs, cs, xp, cp, ns = _frames_args(frames)
+    h = g("encode_gof")(n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after)
+    out = []
+    for f in range(n):
+        fr = GofFrame()
+        w, hh, r = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        g("gof_dims")(h, f, C.byref(w), C.byref(hh), C.byref(r))
+        fr.width, fr.height = w.value, hh.value
+        fr.patches = _collect_patches_borrowed(lib, prefix, g("gof_patches")(h, f))
+        for what, dt in GOF_DTYPES.items():
+            cnt = g("gof_get")(h, f, what, None)
+            a = np.zeros(cnt, dt)
+            if cnt:
+                g("gof_get")(h, f, what, a.ctypes.data_as(C.c_void_p))
+            fr.data[what] = a
+        out.append(fr)
+    g("gof_free")(h)
+    return out
+
+
+def _oracle_encode_gof(self, frames, params, occupancy_precision=4, stop_after=0):
+    return _generic_encode_gof(self.lib._dll, "pcco_", frames, params, occupancy_precision, stop_after)
+
+
+Oracle.encode_gof = _oracle_encode_gof
+GOF_NAMES = {1: "occupancy", 2: "om_video", 3: "block_to_patch", 4: "geo0", 5: "geo1", 6: "rec_xyz", 7: "point_to_pixel", 8: "rec_partition",
+             9: "rec_boundary", 10: "rec_rgb", 11: "attr0_raw", 12: "attr1_raw", 13: "attr0", 14: "attr1"}
+
+
+def compare_gof(got, want, attr_tol=0):
+    """returns a list of mismatch descriptions (empty == parity). attribute planes / colours may differ by <= attr_tol."""
+    bad = []
+    if len(got) != len(want):
+        return ["frame count %d != %d" % (len(got), len(want))]
+    for f, (a, b) in enumerate(zip(got, want)):
+        if (a.width, a.height) != (b.width, b.height):
+            bad.append("frame %d canvas %dx%d != %dx%d" % (f, a.width, a.height, b.width, b.height))
+        if len(a.patches.patches) != len(b.patches.patches):
+            bad.append("frame %d patch count %d != %d" % (f, len(a.patches.patches), len(b.patches.patches)))
+        else:
+            for fld in a.patches.patches.dtype.names:
+                if not np.array_equal(a.patches.patches[fld], b.patches.patches[fld]):
+                    bad.append("frame %d patch field %s" % (f, fld))
+            if not np.array_equal(a.patches.depth, b.patches.depth):
+                bad.append("frame %d patch depth arena" % f)
+            if not np.array_equal(a.patches.occ, b.patches.occ):
+                bad.append("frame %d patch occupancy arena" % f)
+        for what, name in GOF_NAMES.items():
+            x, y = a.data[what], b.data[what]
+            if x.shape != y.shape:
+                bad.append("frame %d %s size %d != %d" % (f, name, x.size, y.size))
+            elif what in (10, 11, 12, 13, 14) and attr_tol > 0:
+                d = np.abs(x.astype(np.int32) - y.astype(np.int32))
+                if d.size and d.max() > attr_tol:
+                    bad.append("frame %d %s max abs diff %d (> %d) at %d samples" % (f, name, d.max(), attr_tol, int((d > attr_tol).sum())))
+            elif not np.array_equal(x, y):
+                bad.append("frame %d %s differs at %d of %d" % (f, name, int((x != y).sum()), x.size))
+    return bad
