@@ -75,7 +75,7 @@ def test_oracle_gof_vs_reference(oracle, reference):
 
 def test_oracle_gof_precision2_vs_reference(oracle, reference):
     frames = [synth.sphere(radius=22, center=70, seed=3)]
-    prm = bindings.ctc_seg_params(bits=10, iterations=5, weight=(1.0, 1.0, 1.0))
+    prm = bindings.ctc_seg_params(bits=10, iterations=5, weight=reference.weight_normal(frames[0][0], 11))
     ref, _ = reference.encode_gof(frames, prm, occupancy_precision=2)
     assert bindings.compare_gof(oracle.encode_gof(frames, prm, occupancy_precision=2), ref) == []
 
