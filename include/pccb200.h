@@ -129,6 +129,45 @@ size_t pccb200_patches_occ_elems( const pccb200_patchlist* pl );
 int    pccb200_patches_get( const pccb200_patchlist* pl, pccb200_patch* patches, int16_t* depth_arena, uint8_t* occ_arena );
 void   pccb200_patches_free( pccb200_patchlist* pl );
 
+/* ---- GOF-level entry points ------------------------------------------------------------------------------
+ * PCCEncoder::encode between the source clouds and the three videoEncoder.compress calls
+ * (PccLibEncoder/source/PCCEncoder.cpp:103-424): generateSegments (:103) -> placeSegments (:110) -> generateOccupancyMap
+ * + generateOccupancyMapVideo (:133,:139) -> generateBlockToPatchFromOccupancyMapVideo (:168) -> generateGeometryVideo
+ * (:172) -> generatePointCloud (:328) -> generateAttributeVideo (:341) -> attribute padding (:344-424), all frames of the
+ * GOF concurrently (one stream per frame). The occupancy/geometry videos are treated as losslessly coded (decoded ==
+ * source), which is what the reference sees for occupancy in CTC and what a passthrough codec gives for geometry.
+ * params->weight_normal must hold pccb200_weight_normal() of frame 0 (PCCEncoder.cpp:4726).
+ * stop_after: 0 = all stages, 1 = after packing, 2 = after the geometry images, 3 = after generatePointCloud.
+ * One GOF is live per context: a later pccb200_encode_gof reuses the device buffers of the earlier one. */
+typedef struct pccb200_gof pccb200_gof;
+int  pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                         const pccb200_seg_params* params, int occupancy_precision, int stop_after, pccb200_gof** out );
+void pccb200_gof_free( pccb200_gof* gof );
+/* canvas size (identical for all frames of the GOF) and number of reconstructed points of frame f */
+int  pccb200_gof_dims( const pccb200_gof* gof, int f, size_t* width, size_t* height, size_t* rec_points );
+/* patches of frame f in PACKED order (the order of tile.getPatches() after packFlexible) with u0/v0/orientation filled;
+ * borrowed: valid until pccb200_gof_free */
+const pccb200_patchlist* pccb200_gof_patches( const pccb200_gof* gof, int f );
+
+/* products of frame f; pccb200_gof_get returns the element count and, when dst != NULL, copies device -> host */
+enum {
+  PCCB200_GOF_OCCUPANCY      = 1,  /* uint8  W*H          PCCFrameContext::occupancyMap_ before generatePointCloud          */
+  PCCB200_GOF_OM_VIDEO       = 2,  /* uint8  (W/p)*(H/p)  luma plane of the occupancy video frame (-> HM)                   */
+  PCCB200_GOF_BLOCK_TO_PATCH = 3,  /* uint32 (W/16)*(H/16) PCCFrameContext::blockToPatch_ (patch index + 1, packed order)   */
+  PCCB200_GOF_GEO0           = 4,  /* uint16 W*H          luma plane of geometry frame 2f   (D0, dilated) (-> HM)           */
+  PCCB200_GOF_GEO1           = 5,  /* uint16 W*H          luma plane of geometry frame 2f+1 (D1, dilated) (-> HM)           */
+  PCCB200_GOF_REC_XYZ        = 6,  /* int16  R*3          reconstructed positions, reference emission order                 */
+  PCCB200_GOF_POINT_TO_PIXEL = 7,  /* uint32 R*3          PCCFrameContext::pointToPixel_ (x, y, map)                        */
+  PCCB200_GOF_REC_PARTITION  = 8,  /* uint32 R            patch index (packed order) of every reconstructed point           */
+  PCCB200_GOF_REC_BOUNDARY   = 9,  /* uint16 R            PCCPointSet3 boundary point type after identifyBoundaryPoints     */
+  PCCB200_GOF_REC_RGB        = 10, /* uint8  R*3          colours after transferColors                                      */
+  PCCB200_GOF_ATTR0_RAW      = 11, /* uint16 3*W*H planar R,G,B: attribute frame 2f   before padding                        */
+  PCCB200_GOF_ATTR1_RAW      = 12, /* uint16 3*W*H        attribute frame 2f+1 before padding                               */
+  PCCB200_GOF_ATTR0          = 13, /* uint16 3*W*H        attribute frame 2f   after push-pull padding (-> colour conversion -> HM) */
+  PCCB200_GOF_ATTR1          = 14  /* uint16 3*W*H        attribute frame 2f+1 after push-pull padding                      */
+};
+size_t pccb200_gof_get( pccb200_gof* gof, int f, int what, void* dst );
+
 #ifdef __cplusplus
 }
 #endif

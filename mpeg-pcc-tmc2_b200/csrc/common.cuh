@@ -34,6 +34,15 @@ struct DevBuf {
   DevBuf()   = default;
   DevBuf( const DevBuf& )            = delete;
   DevBuf& operator=( const DevBuf& ) = delete;
+  DevBuf( DevBuf&& o ) noexcept : p( o.p ), cap( o.cap ) { o.p = nullptr, o.cap = 0; }
+  DevBuf& operator=( DevBuf&& o ) noexcept {
+    if ( this != &o ) {
+      release();
+      p = o.p, cap = o.cap;
+      o.p = nullptr, o.cap = 0;
+    }
+    return *this;
+  }
   ~DevBuf() { release(); }
   void release() {
     if ( p ) cudaFree( p );

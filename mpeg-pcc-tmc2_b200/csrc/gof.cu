@@ -1,0 +1,377 @@
+// gof.cu — GOF-level entry points: the stages of PCCEncoder::encode between `sources` and the three
+// videoEncoder.compress calls (PccLibEncoder/source/PCCEncoder.cpp:103-424), for all frames of a GOF.
+//
+// Frames of a GOF are independent up to the canvas size (the reference itself runs them under tbb::parallel_for,
+// PCCEncoder.cpp:4729-4747, 6670-6729, 344-420), so every frame gets its own CUDA stream, device buffers and host worker
+// thread; the GPU overlaps the frames' kernels — in particular the latency-bound orientation walk (orient.cu), which
+// occupies one warp per frame, overlaps with the bandwidth-bound stages of the other frames.
+#include <algorithm>
+#include <cmath>
+#include <thread>
+
+#include "stages.cuh"
+
+using namespace pccb200;
+
+#include "ctx.cuh"
+
+struct FrameState {
+  cudaStream_t     stream = nullptr;
+  const int16_t*   hXyz   = nullptr;
+  const uint8_t*   hRgb   = nullptr;
+  size_t           n      = 0;
+  DevBuf<int16_t>  xyzRaw;
+  DevBuf<uint8_t>  rgbRaw, partition;
+  DevBuf<short4>   xyz4;
+  DevBuf<uchar4>   rgb4, recRgb;
+  KdTree           tree;
+  DevBuf<uint32_t> nbr;
+  DevBuf<double>   normals;
+  OrientScratch    orient;
+  RefineScratch    refine;
+  PatchScratch     patch;
+  PatchResult      seg;  // patches in creation order + device arenas
+  // canvas
+  std::vector<pccb200_patch> packed;  // packed (sorted) order, u0/v0/orientation filled
+  DevBuf<CanvasPatch>        dPatches;
+  DevBuf<long long>          elemBase;
+  DevBuf<int>                packResult;
+  long long                  totalElems = 0;
+  int                        heightPx = 0, maxPatchPixels = 1, maxPatchBlocks = 1;
+  CanvasImages               im;
+  ReconScratch               rc;
+  ColorScratch               color;
+  AttrImages                 attr;
+  Profiler                   prof;
+  int                        status = 0;
+  std::string                error;
+  ~FrameState() {
+    if ( stream ) cudaStreamDestroy( stream );
+  }
+};
+
+pccb200_ctx::~pccb200_ctx() {}
+
+struct pccb200_gof {
+  pccb200_ctx*                   ctx = nullptr;
+  int                            nframes = 0, occPrec = 4, stage = 0;
+  pccb200_seg_params             prm;
+  size_t                         W = 0, H = 0;
+  std::vector<FrameState*>       frames;
+  std::vector<pccb200_patchlist> lists;  // host copies of the packed patch lists
+};
+
+namespace {
+
+template <class F>
+int forEachFrame( pccb200_gof* g, F&& fn ) {
+  std::vector<std::thread> workers;
+  workers.reserve( g->nframes );
+  for ( int f = 0; f < g->nframes; ++f ) {
+    workers.emplace_back( [g, f, &fn]() {
+      FrameState& fs = *g->frames[f];
+      try {
+        PCC_CUDA( cudaSetDevice( g->ctx->device ) );
+        fn( fs, f );
+        PCC_CUDA( cudaStreamSynchronize( fs.stream ) );
+      } catch ( const CudaError& e ) {
+        char buf[512];
+        snprintf( buf, sizeof( buf ), "frame %d: CUDA error %d (%s) at %s:%d", f, int( e.code ), cudaGetErrorString( e.code ), e.file, e.line );
+        fs.error  = buf;
+        fs.status = PCCB200_ERR_CUDA;
+        cudaGetLastError();
+      } catch ( const std::exception& e ) {
+        fs.error  = e.what();
+        fs.status = PCCB200_ERR_CUDA;
+      }
+    } );
+  }
+  for ( auto& w : workers ) w.join();
+  for ( int f = 0; f < g->nframes; ++f )
+    if ( g->frames[f]->status != 0 ) {
+      g->ctx->lastError = g->frames[f]->error;
+      return g->frames[f]->status;
+    }
+  return PCCB200_OK;
+}
+
+// a1..a11 for one frame (PCCPatchSegmenter3::compute)
+void segmentFrame( FrameState& fs, const pccb200_seg_params& prm ) {
+  cudaStream_t s = fs.stream;
+  const size_t n = fs.n;
+  const int    k = 16;
+  Profiler*    pf = &fs.prof;
+  fs.seg.patches.clear();
+  fs.seg.depthElems = fs.seg.occElems = 0;
+  if ( n == 0 ) return;
+  {
+    ProfScope t( pf, "h2d", s );
+    fs.xyzRaw.reserve( 3 * n ), fs.rgbRaw.reserve( 3 * n ), fs.xyz4.reserve( n ), fs.rgb4.reserve( n ), fs.partition.reserve( n );
+    PCC_CUDA( cudaMemcpyAsync( fs.xyzRaw, fs.hXyz, 3 * n * sizeof( int16_t ), cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( fs.rgbRaw, fs.hRgb, 3 * n, cudaMemcpyHostToDevice, s ) );
+    packXyz( fs.xyzRaw, n, fs.xyz4, s );
+    packRgb( fs.rgbRaw, n, fs.rgb4, s );
+  }
+  {
+    ProfScope t( pf, "kdtree_build", s );
+    kdBuild( fs.tree, fs.xyz4, n, s );
+  }
+  fs.nbr.reserve( n * k + 1 ), fs.normals.reserve( 3 * n );
+  {
+    ProfScope t( pf, "knn16", s );
+    kdKnn( fs.tree, fs.xyz4, n, fs.tree.vind, k, fs.nbr, nullptr, s );
+  }
+  {
+    ProfScope t( pf, "normals", s );
+    computeNormals( fs.xyz4, fs.nbr, k, n, fs.normals, s );
+  }
+  if ( prm.normal_orientation == 1 ) {
+    ProfScope t( pf, "orient", s );
+    fs.orient.prof = pf;
+    orientNormals( fs.orient, fs.xyz4, fs.nbr, k, n, fs.normals, s );
+  }
+  {
+    ProfScope t( pf, "initial_seg", s );
+    initialSegmentation( fs.normals, n, prm.weight_normal, fs.partition, s );
+  }
+  {
+    ProfScope t( pf, "refine", s );
+    refineSegmentation( fs.refine, fs.xyz4, fs.normals, n, prm, fs.partition, s );
+  }
+  {
+    ProfScope t( pf, "patches", s );
+    segmentPatches( fs.patch, fs.seg, fs.xyz4, fs.rgb4, fs.nbr, k, fs.partition, n, prm, s );
+  }
+}
+
+// PCCPatch::gt (PccLibCommon/source/PCCPatch.cpp:349-371): a strict total order, so any sort reproduces std::sort
+bool patchBefore( const pccb200_patch& a, const pccb200_patch& b ) {
+  const int amax = std::max( a.size_u0, a.size_v0 ), amin = std::min( a.size_u0, a.size_v0 );
+  const int bmax = std::max( b.size_u0, b.size_v0 ), bmin = std::min( b.size_u0, b.size_v0 );
+  return amax != bmax ? amax > bmax : ( amin != bmin ? amin > bmin : a.index < b.index );
+}
+
+// a13 for one frame: sort (KB of metadata, host) + first-fit placement (device)
+void packFrame( FrameState& fs, const pccb200_seg_params& prm, int presetWidth, int presetHeight, int numTilesHor, double tileRatio ) {
+  cudaStream_t s = fs.stream;
+  ProfScope    t( &fs.prof, "pack", s );
+  fs.packed   = fs.seg.patches;
+  fs.heightPx = presetHeight;
+  const int P = int( fs.packed.size() );
+  fs.totalElems = 0, fs.maxPatchPixels = 1, fs.maxPatchBlocks = 1;
+  if ( P == 0 ) return;
+  std::sort( fs.packed.begin(), fs.packed.end(), patchBefore );
+  const int occRes = prm.occupancy_resolution;
+  int       sizeU = presetWidth / occRes, sizeV = std::max( fs.packed[0].size_v0, fs.packed[0].size_u0 );
+  for ( auto& p : fs.packed ) sizeU = std::max( sizeU, p.size_u0 + 1 );
+  const int tileW = sizeU / numTilesHor, tileH = int( tileW * tileRatio );
+  sizeV           = sizeV >= tileH ? sizeV : tileH;
+  std::vector<CanvasPatch> cp( P );
+  std::vector<long long>   base( P + 1 );
+  for ( int i = 0; i < P; ++i ) {
+    const pccb200_patch& m = fs.packed[i];
+    CanvasPatch&         c = cp[i];
+    c.viewId = m.view_id, c.u1 = m.u1, c.v1 = m.v1, c.d1 = m.d1, c.sizeU = m.size_u, c.sizeV = m.size_v;
+    c.sizeU0 = m.size_u0, c.sizeV0 = m.size_v0, c.u0 = c.v0 = c.orientation = 0, c.pad = 0;
+    c.depthOff = m.depth_offset, c.occOff = m.occ_offset;
+    base[i]    = fs.totalElems;
+    fs.totalElems += (long long)m.size_u0 * m.size_v0 * occRes * occRes;
+    fs.maxPatchPixels = std::max( fs.maxPatchPixels, m.size_u * m.size_v );
+    fs.maxPatchBlocks = std::max( fs.maxPatchBlocks, m.size_u0 * m.size_v0 );
+  }
+  base[P] = fs.totalElems;
+  fs.dPatches.reserve( P ), fs.elemBase.reserve( P + 1 ), fs.packResult.reserve( 4 );
+  PCC_CUDA( cudaMemcpyAsync( fs.dPatches, cp.data(), P * sizeof( CanvasPatch ), cudaMemcpyHostToDevice, s ) );
+  PCC_CUDA( cudaMemcpyAsync( fs.elemBase, base.data(), ( P + 1 ) * sizeof( long long ), cudaMemcpyHostToDevice, s ) );
+  const int rc = packPatches( fs.dPatches, P, fs.seg.occ, sizeU, sizeV, occRes, fs.packResult, s );
+  if ( rc != PCCB200_OK ) throw std::runtime_error( "canvas wider than the packer supports" );
+  int res[2] = { 0, 0 };
+  PCC_CUDA( cudaMemcpyAsync( cp.data(), fs.dPatches, P * sizeof( CanvasPatch ), cudaMemcpyDeviceToHost, s ) );
+  PCC_CUDA( cudaMemcpyAsync( res, fs.packResult, sizeof( res ), cudaMemcpyDeviceToHost, s ) );
+  PCC_CUDA( cudaStreamSynchronize( s ) );
+  if ( res[1] ) throw std::runtime_error( "patch packing exceeded the maximum canvas height" );
+  for ( int i = 0; i < P; ++i ) fs.packed[i].u0 = cp[i].u0, fs.packed[i].v0 = cp[i].v0, fs.packed[i].orientation = cp[i].orientation;
+  fs.heightPx = res[0];
+}
+
+size_t copyOut( void* dst, const void* dev, size_t elems, size_t elemBytes, cudaStream_t s ) {
+  if ( dst && elems ) {
+    PCC_CUDA( cudaMemcpyAsync( dst, dev, elems * elemBytes, cudaMemcpyDeviceToHost, s ) );
+    PCC_CUDA( cudaStreamSynchronize( s ) );
+  }
+  return elems;
+}
+
+__global__ void kUnpackXyz( const short4* __restrict__ in, int n, int16_t* __restrict__ out ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i < n ) out[3 * size_t( i )] = in[i].x, out[3 * size_t( i ) + 1] = in[i].y, out[3 * size_t( i ) + 2] = in[i].z;
+}
+__global__ void kUnpackRgb( const uchar4* __restrict__ in, int n, uint8_t* __restrict__ out ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i < n ) out[3 * size_t( i )] = in[i].x, out[3 * size_t( i ) + 1] = in[i].y, out[3 * size_t( i ) + 2] = in[i].z;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                        const pccb200_seg_params* prm, int occupancyPrecision, int stopAfter, pccb200_gof** out ) {
+  if ( !ctx || !out || nframes < 0 || ( nframes > 0 && ( !xyz || !rgb || !n ) ) || !prm ) return PCCB200_ERR_BAD_ARG;
+  if ( prm->nn_normal_estimation != 16 || prm->max_nn_count_patch_seg != 16 || prm->geometry_bitdepth_3d > 12 || prm->occupancy_resolution != 16 ||
+       ( prm->normal_orientation != 0 && prm->normal_orientation != 1 ) || occupancyPrecision < 1 || 16 % occupancyPrecision != 0 ||
+       prm->map_count_minus1 != 1 )
+    return PCCB200_ERR_UNSUPPORTED;
+  *out = nullptr;
+  return guarded( ctx, [&]() -> int {
+    pccb200_gof* g = new pccb200_gof();
+    g->ctx = ctx, g->nframes = nframes, g->occPrec = occupancyPrecision, g->prm = *prm;
+    while ( int( ctx->framePool.size() ) < nframes ) {
+      ctx->framePool.emplace_back( new FrameState() );
+      PCC_CUDA( cudaStreamCreateWithFlags( &ctx->framePool.back()->stream, cudaStreamNonBlocking ) );
+    }
+    for ( int f = 0; f < nframes; ++f ) {
+      FrameState* fs = ctx->framePool[f].get();
+      fs->hXyz = xyz[f], fs->hRgb = rgb[f], fs->n = n[f], fs->status = 0, fs->error.clear();
+      fs->prof.enabled = ctx->prof.enabled;
+      g->frames.push_back( fs );
+    }
+    const int minW = prm->geometry_bitdepth_3d > 11 ? 2560 : 1280, minH = 1280;  // minimumImageWidth/Height (cfg/sequence/*_vox11.cfg: 2560)
+    int       rc   = forEachFrame( g, [&]( FrameState& fs, int ) {
+      segmentFrame( fs, g->prm );
+      packFrame( fs, g->prm, minW, minH, 2, 1.0 );
+    } );
+    if ( rc != PCCB200_OK ) {
+      delete g;
+      return rc;
+    }
+    // a14: one canvas size per GOF (PCCEncoder::resizeTileGeometryVideo + resizeGeometryVideo, PCCEncoder.cpp:5546-5634)
+    size_t W = minW, H = minH;
+    for ( auto* fs : g->frames ) H = std::max( H, size_t( fs->heightPx ) );
+    g->W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), g->H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
+    g->stage = 1;
+    const int Wi = int( g->W ), Hi = int( g->H );
+    if ( stopAfter != 1 ) {
+      rc = forEachFrame( g, [&]( FrameState& fs, int ) {
+        cudaStream_t s = fs.stream;
+        {
+          ProfScope t( &fs.prof, "images", s );
+          formOccupancyAndGeometry( fs.dPatches, int( fs.packed.size() ), fs.maxPatchPixels, fs.maxPatchBlocks, fs.seg.depth, g->prm.occupancy_resolution,
+                                    g->occPrec, Wi, Hi, fs.im, s );
+        }
+        int err = 0;
+        PCC_CUDA( cudaMemcpyAsync( &err, fs.im.error, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+        PCC_CUDA( cudaStreamSynchronize( s ) );
+        if ( err ) throw std::runtime_error( "patch2Canvas out of the canvas" );
+        if ( stopAfter == 2 ) return;
+        // the occupancy and geometry videos are coded losslessly / passed through here: decoded == source
+        {
+          ProfScope t( &fs.prof, "reconstruct", s );
+          reconstructPoints( fs.dPatches, fs.elemBase, int( fs.packed.size() ), fs.totalElems, g->prm.occupancy_resolution, g->occPrec, Wi, Hi, fs.im.om,
+                             fs.im.blockToPatch, fs.im.geo0, fs.im.geo1, fs.rc, s );
+        }
+        if ( stopAfter == 3 ) return;
+        const size_t R = fs.rc.numPoints;
+        fs.recRgb.reserve( R + 1 );
+        {
+          ProfScope t( &fs.prof, "color_transfer", s );
+          transferColors( fs.color, fs.tree, fs.xyz4, fs.rgb4, fs.n, fs.rc.recXyz, R, fs.recRgb, s );
+        }
+        {
+          ProfScope t( &fs.prof, "attribute_images", s );
+          formAttributeImages( fs.rc.pointToPixel, fs.recRgb, R, fs.im.om, Wi, Hi, g->occPrec, fs.attr, s );
+        }
+      } );
+      if ( rc != PCCB200_OK ) {
+        delete g;
+        return rc;
+      }
+      g->stage = stopAfter == 2 ? 2 : ( stopAfter == 3 ? 3 : 4 );
+    }
+    // host copies of the packed patch lists (KBs of metadata + the per-patch maps downstream reference code reads)
+    g->lists.resize( nframes );
+    rc = forEachFrame( g, [&]( FrameState& fs, int f ) {
+      pccb200_patchlist& pl = g->lists[f];
+      pl.patches            = fs.packed;
+      pl.depth.resize( fs.seg.depthElems ), pl.occ.resize( fs.seg.occElems );
+      ProfScope t( &fs.prof, "d2h_patches", fs.stream );
+      if ( fs.seg.depthElems ) PCC_CUDA( cudaMemcpyAsync( pl.depth.data(), fs.seg.depth, fs.seg.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, fs.stream ) );
+      if ( fs.seg.occElems ) PCC_CUDA( cudaMemcpyAsync( pl.occ.data(), fs.seg.occ, fs.seg.occElems, cudaMemcpyDeviceToHost, fs.stream ) );
+    } );
+    for ( auto* fs : g->frames ) {
+      fs->prof.collect( fs->stream );
+      for ( auto& r : fs->prof.results ) ctx->prof.results.push_back( r );
+      fs->prof.results.clear();
+    }
+    if ( rc != PCCB200_OK ) {
+      delete g;
+      return rc;
+    }
+    *out = g;
+    return PCCB200_OK;
+  } );
+}
+
+void pccb200_gof_free( pccb200_gof* g ) { delete g; }
+
+int pccb200_gof_dims( const pccb200_gof* g, int f, size_t* w, size_t* h, size_t* recPoints ) {
+  if ( !g || f < 0 || f >= g->nframes ) return PCCB200_ERR_BAD_ARG;
+  if ( w ) *w = g->W;
+  if ( h ) *h = g->H;
+  if ( recPoints ) *recPoints = g->stage >= 3 ? g->frames[f]->rc.numPoints : 0;
+  return PCCB200_OK;
+}
+
+const pccb200_patchlist* pccb200_gof_patches( const pccb200_gof* g, int f ) {
+  if ( !g || f < 0 || f >= g->nframes ) return nullptr;
+  return &g->lists[f];
+}
+
+size_t pccb200_gof_get( pccb200_gof* g, int f, int what, void* dst ) {
+  if ( !g || f < 0 || f >= g->nframes ) return 0;
+  FrameState&  fs = *g->frames[f];
+  cudaStream_t s  = fs.stream;
+  size_t       result = 0;
+  guarded( g->ctx, [&]() -> int {
+    const size_t Q = g->W * g->H, cells = ( g->W / g->occPrec ) * ( g->H / g->occPrec ), blocks = ( g->W / 16 ) * ( g->H / 16 );
+    const size_t R = g->stage >= 3 ? fs.rc.numPoints : 0;
+    if ( what >= 1 && what <= 5 && g->stage < 2 ) return 0;
+    if ( what >= 6 && what <= 9 && g->stage < 3 ) return 0;
+    if ( what >= 10 && g->stage < 4 ) return 0;
+    switch ( what ) {
+      case PCCB200_GOF_OCCUPANCY: result = copyOut( dst, fs.im.occ, Q, 1, s ); break;
+      case PCCB200_GOF_OM_VIDEO: result = copyOut( dst, fs.im.om, cells, 1, s ); break;
+      case PCCB200_GOF_BLOCK_TO_PATCH: result = copyOut( dst, fs.im.blockToPatch, blocks, 4, s ); break;
+      case PCCB200_GOF_GEO0: result = copyOut( dst, fs.im.geo0, Q, 2, s ); break;
+      case PCCB200_GOF_GEO1: result = copyOut( dst, fs.im.geo1, Q, 2, s ); break;
+      case PCCB200_GOF_REC_XYZ:
+        if ( dst && R ) {
+          fs.xyzRaw.reserve( 3 * R );
+          kUnpackXyz<<<divUp( R, 256 ), 256, 0, s>>>( fs.rc.recXyz, int( R ), fs.xyzRaw );
+          copyOut( dst, fs.xyzRaw, 3 * R, 2, s );
+        }
+        result = 3 * R;
+        break;
+      case PCCB200_GOF_POINT_TO_PIXEL: result = copyOut( dst, fs.rc.pointToPixel, 3 * R, 4, s ); break;
+      case PCCB200_GOF_REC_PARTITION: result = copyOut( dst, fs.rc.recPartition, R, 4, s ); break;
+      case PCCB200_GOF_REC_BOUNDARY: result = copyOut( dst, fs.rc.boundary, R, 2, s ); break;
+      case PCCB200_GOF_REC_RGB:
+        if ( dst && R ) {
+          fs.rgbRaw.reserve( 3 * R );
+          kUnpackRgb<<<divUp( R, 256 ), 256, 0, s>>>( fs.recRgb, int( R ), fs.rgbRaw );
+          copyOut( dst, fs.rgbRaw, 3 * R, 1, s );
+        }
+        result = 3 * R;
+        break;
+      case PCCB200_GOF_ATTR0_RAW: result = copyOut( dst, fs.attr.rawPlanes[0], 3 * Q, 2, s ); break;
+      case PCCB200_GOF_ATTR1_RAW: result = copyOut( dst, fs.attr.rawPlanes[1], 3 * Q, 2, s ); break;
+      case PCCB200_GOF_ATTR0: result = copyOut( dst, fs.attr.planes[0], 3 * Q, 2, s ); break;
+      case PCCB200_GOF_ATTR1: result = copyOut( dst, fs.attr.planes[1], 3 * Q, 2, s ); break;
+      default: break;
+    }
+    return 0;
+  } );
+  return result;
+}
+
+}  // extern "C"

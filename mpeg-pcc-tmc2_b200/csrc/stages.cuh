@@ -58,6 +58,50 @@ void packRgb( const uint8_t* rgb3, size_t n, uchar4* out, cudaStream_t s );
 void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, const uchar4* rgb, const uint32_t* nbr, int k,
                      const uint8_t* partition, size_t n, const pccb200_seg_params& prm, cudaStream_t s );
 
+// canvas.cu
+struct CanvasPatch {  // device-side patch record in packed order
+  int       viewId, u1, v1, d1, sizeU, sizeV, sizeU0, sizeV0, u0, v0, orientation, pad;
+  long long depthOff, occOff;
+};
+struct CanvasImages {
+  DevBuf<uint8_t>  occ, om, blockEmpty;
+  DevBuf<uint16_t> geo0, geo1;
+  DevBuf<uint32_t> blockToPatch;
+  DevBuf<int>      error;
+};
+struct ReconScratch {
+  DevBuf<uint32_t> counts, offsets, scanTmp, pointToPixel, recPartition;
+  DevBuf<short4>   recXyz;
+  DevBuf<uint16_t> boundary;
+  size_t           numPoints = 0;
+};
+struct AttrImages {
+  DevBuf<ushort4>               T[2], tmp;
+  DevBuf<uint8_t>               occ;
+  DevBuf<uint16_t>              rawPlanes[2], planes[2];
+  std::vector<DevBuf<ushort4>>  mip;
+  std::vector<DevBuf<uint8_t>>  mipOcc;
+};
+int    packPatches( CanvasPatch* dPatches, int numPatches, const uint8_t* occArena, int sizeU, int sizeV, int occRes, int* dResult, cudaStream_t s );
+void   formOccupancyAndGeometry( const CanvasPatch* dPatches, int numPatches, int maxPatchPixels, int maxPatchBlocks, const int16_t* depthArena,
+                                 int occRes, int prec, int W, int H, CanvasImages& im, cudaStream_t s );
+size_t reconstructPoints( const CanvasPatch* dPatches, const long long* dElemBase, int numPatches, long long totalElems, int occRes, int prec, int W,
+                          int H, const uint8_t* om, const uint32_t* blockToPatch, const uint16_t* geo0, const uint16_t* geo1, ReconScratch& rc,
+                          cudaStream_t s );
+void   formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, size_t R, const uint8_t* om, int W, int H, int prec, AttrImages& at,
+                            cudaStream_t s );
+
+// color.cu
+struct ColorScratch {
+  KdTree           recTree;
+  DevBuf<uint32_t> fwdIdx, bwdIdx, idsA, idsB;
+  DevBuf<float>    fwdDist, bwdDist;
+  DevBuf<uint64_t> keysA, keysB;
+  DevBuf<uint8_t>  cubTmp;
+};
+void transferColors( ColorScratch& sc, const KdTree& srcTree, const short4* srcPts, const uchar4* srcRgb, size_t n, const short4* recPts, size_t R,
+                     uchar4* recRgb, cudaStream_t s );
+
 // util.cu
 void projectedAreas( const short4* pts, size_t n, int bits, uint32_t* faces, unsigned* counts, cudaStream_t s );
 void gatherU8( const uint8_t* src, const uint32_t* idx, size_t n, uint8_t* dst, cudaStream_t s );

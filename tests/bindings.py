@@ -544,3 +544,46 @@ def compare_gof(got, want, attr_tol=0):
             elif not np.array_equal(x, y):
                 bad.append("frame %d %s differs at %d of %d" % (f, name, int((x != y).sum()), x.size))
     return bad
+
+
+def _product_encode_gof(self, frames, params, occupancy_precision=4, stop_after=0, fetch=None):
+    """libpccb200 GOF entry point; returns list of GofFrame like Oracle.encode_gof. fetch: iterable of GOF_* ids (default all)."""
+    L = self.lib
+    L.pccb200_encode_gof.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_i16p), C.POINTER(c_u8p), C.POINTER(C.c_size_t), C.POINTER(SegParams),
+                                     C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.pccb200_gof_free.argtypes = [C.c_void_p]
+    L.pccb200_gof_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.pccb200_gof_patches.restype = C.c_void_p
+    L.pccb200_gof_patches.argtypes = [C.c_void_p, C.c_int]
+    L.pccb200_gof_get.restype = C.c_size_t
+    L.pccb200_gof_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    n, xs, cs, xp, cp, ns = _frames_args(frames)
+    h = C.c_void_p()
+    self._check(L.pccb200_encode_gof(self.ctx, n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after, C.byref(h)))
+    out = []
+    for f in range(n):
+        fr = GofFrame()
+        w, hh, r = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        L.pccb200_gof_dims(h, f, C.byref(w), C.byref(hh), C.byref(r))
+        fr.width, fr.height = w.value, hh.value
+        pl = L.pccb200_gof_patches(h, f)
+        cnt = L.pccb200_patches_count(pl)
+        patches = np.zeros(cnt, dtype=PATCH_DTYPE)
+        depth = np.zeros(L.pccb200_patches_depth_elems(pl), np.int16)
+        occ = np.zeros(L.pccb200_patches_occ_elems(pl), np.uint8)
+        self._check(L.pccb200_patches_get(pl, patches.ctypes.data_as(C.c_void_p), ptr(depth, c_i16p), ptr(occ, c_u8p)))
+        fr.patches = PatchSet(patches, depth, occ)
+        for what, dt in GOF_DTYPES.items():
+            if fetch is not None and what not in fetch:
+                continue
+            cnt = L.pccb200_gof_get(h, f, what, None)
+            a = np.zeros(cnt, dt)
+            if cnt:
+                L.pccb200_gof_get(h, f, what, a.ctypes.data_as(C.c_void_p))
+            fr.data[what] = a
+        out.append(fr)
+    L.pccb200_gof_free(h)
+    return out
+
+
+Product.encode_gof = _product_encode_gof
