@@ -6,6 +6,42 @@
 
 #include "stages.cuh"
 
+// per-frame device state of a GOF (gof.cu); pooled in the context and reused by successive GOFs
+struct FrameState {
+  cudaStream_t     stream = nullptr;
+  const int16_t*   hXyz   = nullptr;
+  const uint8_t*   hRgb   = nullptr;
+  size_t           n      = 0;
+  DevBuf<int16_t>  xyzRaw;
+  DevBuf<uint8_t>  rgbRaw, partition;
+  DevBuf<short4>   xyz4;
+  DevBuf<uchar4>   rgb4, recRgb;
+  KdTree           tree;
+  DevBuf<uint32_t> nbr;
+  DevBuf<double>   normals;
+  OrientScratch    orient;
+  RefineScratch    refine;
+  PatchScratch     patch;
+  PatchResult      seg;  // patches in creation order + device arenas
+  // canvas
+  std::vector<pccb200_patch> packed;  // packed (sorted) order, u0/v0/orientation filled
+  DevBuf<CanvasPatch>        dPatches;
+  DevBuf<long long>          elemBase;
+  DevBuf<int>                packResult;
+  long long                  totalElems = 0;
+  int                        heightPx = 0, maxPatchPixels = 1, maxPatchBlocks = 1;
+  CanvasImages               im;
+  ReconScratch               rc;
+  ColorScratch               color;
+  AttrImages                 attr;
+  Profiler                   prof;
+  int                        status = 0;
+  std::string                error;
+  ~FrameState() {
+    if ( stream ) cudaStreamDestroy( stream );
+  }
+};
+
 struct pccb200_ctx {
   int              device = 0;
   cudaStream_t     stream = nullptr;
@@ -25,7 +61,7 @@ struct pccb200_ctx {
   OrientScratch    orient;
   RefineScratch    refine;
   PatchScratch     patch;
-  std::vector<std::unique_ptr<struct FrameState>> framePool;  // reused by successive GOFs (gof.cu)
+  std::vector<std::unique_ptr<FrameState>> framePool;  // reused by successive GOFs (gof.cu)
   ~pccb200_ctx();
 };
 

@@ -7,6 +7,7 @@
 // occupies one warp per frame, overlaps with the bandwidth-bound stages of the other frames.
 #include <algorithm>
 #include <cmath>
+#include <stdexcept>
 #include <thread>
 
 #include "stages.cuh"
@@ -14,41 +15,6 @@
 using namespace pccb200;
 
 #include "ctx.cuh"
-
-struct FrameState {
-  cudaStream_t     stream = nullptr;
-  const int16_t*   hXyz   = nullptr;
-  const uint8_t*   hRgb   = nullptr;
-  size_t           n      = 0;
-  DevBuf<int16_t>  xyzRaw;
-  DevBuf<uint8_t>  rgbRaw, partition;
-  DevBuf<short4>   xyz4;
-  DevBuf<uchar4>   rgb4, recRgb;
-  KdTree           tree;
-  DevBuf<uint32_t> nbr;
-  DevBuf<double>   normals;
-  OrientScratch    orient;
-  RefineScratch    refine;
-  PatchScratch     patch;
-  PatchResult      seg;  // patches in creation order + device arenas
-  // canvas
-  std::vector<pccb200_patch> packed;  // packed (sorted) order, u0/v0/orientation filled
-  DevBuf<CanvasPatch>        dPatches;
-  DevBuf<long long>          elemBase;
-  DevBuf<int>                packResult;
-  long long                  totalElems = 0;
-  int                        heightPx = 0, maxPatchPixels = 1, maxPatchBlocks = 1;
-  CanvasImages               im;
-  ReconScratch               rc;
-  ColorScratch               color;
-  AttrImages                 attr;
-  Profiler                   prof;
-  int                        status = 0;
-  std::string                error;
-  ~FrameState() {
-    if ( stream ) cudaStreamDestroy( stream );
-  }
-};
 
 pccb200_ctx::~pccb200_ctx() {}
 
