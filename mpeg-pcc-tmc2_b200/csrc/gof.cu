@@ -259,10 +259,24 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
     rc = forEachFrame( g, [&]( FrameState& fs, int f ) {
       pccb200_patchlist& pl = g->lists[f];
       pl.patches            = fs.packed;
+      std::vector<int16_t> depth( fs.seg.depthElems );
+      std::vector<uint8_t> occ( fs.seg.occElems );
+      {
+        ProfScope t( &fs.prof, "d2h_patches", fs.stream );
+        if ( fs.seg.depthElems ) PCC_CUDA( cudaMemcpyAsync( depth.data(), fs.seg.depth, fs.seg.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, fs.stream ) );
+        if ( fs.seg.occElems ) PCC_CUDA( cudaMemcpyAsync( occ.data(), fs.seg.occ, fs.seg.occElems, cudaMemcpyDeviceToHost, fs.stream ) );
+        PCC_CUDA( cudaStreamSynchronize( fs.stream ) );
+      }
+      // the device arenas are in creation order; hand the maps out in packed order (the order of the patch records)
       pl.depth.resize( fs.seg.depthElems ), pl.occ.resize( fs.seg.occElems );
-      ProfScope t( &fs.prof, "d2h_patches", fs.stream );
-      if ( fs.seg.depthElems ) PCC_CUDA( cudaMemcpyAsync( pl.depth.data(), fs.seg.depth, fs.seg.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, fs.stream ) );
-      if ( fs.seg.occElems ) PCC_CUDA( cudaMemcpyAsync( pl.occ.data(), fs.seg.occ, fs.seg.occElems, cudaMemcpyDeviceToHost, fs.stream ) );
+      size_t dOff = 0, oOff = 0;
+      for ( auto& m : pl.patches ) {
+        const size_t px = 2 * size_t( m.size_u ) * m.size_v, nb = size_t( m.size_u0 ) * m.size_v0;
+        std::copy( depth.begin() + m.depth_offset, depth.begin() + m.depth_offset + px, pl.depth.begin() + dOff );
+        std::copy( occ.begin() + m.occ_offset, occ.begin() + m.occ_offset + nb, pl.occ.begin() + oOff );
+        m.depth_offset = int64_t( dOff ), m.occ_offset = int64_t( oOff );
+        dOff += px, oOff += nb;
+      }
     } );
     for ( auto* fs : g->frames ) {
       fs->prof.collect( fs->stream );
