@@ -1,16 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — Mpoints/s of the V-PCC patch-generation (+ image-formation, as stages land) hot path.
+"""bench.py — Mpoints/s of the V-PCC patch-generation + image-formation hot path (SURVEY.md §8a rows a1–a26).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--frames F] [--scale S]
 
-One "step" = one GOF-sized batch of F synthetic longdress-like frames (tests/synth.py `figure`, 10-bit,
-~0.8 M points/frame at scale 1.0) pushed through the hot path.  No dataset ships with the reference, so the data is
-synthetic and says so.  Multi-GPU: one process per GPU (torchrun), every rank works on its own batch (weak scaling),
-no data-path collective; the timed region is bracketed by barriers and the max over ranks is reported.
+One "step" = one GOF-sized batch of F synthetic longdress-like frames (tests/synth.py `figure`, 10-bit, ≈0.83 M points
+per frame at the default scale) pushed through the whole hot path: generateSegments, placeSegments, occupancy / geometry
+image formation, generatePointCloud, colour transfer, attribute image formation and padding (PCCEncoder.cpp:103-424,
+the three videoEncoder.compress calls excluded, occupancy/geometry video treated as lossless).  No dataset ships with
+the reference, so the data is synthetic and says so.
 
-JSON line keys follow the driver contract: value = device-timeline throughput with inputs resident in HBM (sum of
-the per-stage CUDA-event spans without the H2D/D2H spans), e2e = wall clock through the C ABI with host buffers,
-roofline = dominant kernel/stage, cpu_baseline = the reference's own CPU code (oracle/_ref) on a bounded sample.
+Multi-GPU (torchrun, one process per GPU): the frames of every GOF are sharded over the ranks (rank r takes F frames of
+an N*F-frame GOF: weak scaling); the one cross-frame coupling of the all-intra path — the common canvas size — is one
+NCCL all-reduce(MAX) of two integers between packing and image formation.  Timing: barrier + synchronize on both sides,
+max over ranks.
+
+JSON keys follow the driver contract.  value = throughput over the DEVICE window (first compute span to last span of any
+frame stream, CUDA events; input already uploaded), e2e = wall clock through the C ABI with host buffers including the
+H2D of the clouds and the D2H of every frame handed to the video codec, roofline = dominant kernel, cpu_baseline = the
+reference's own CPU code (oracle/_ref) on a bounded sample.
 """
 import argparse
 import json
@@ -25,17 +32,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
-STAGES = ["kd-tree build", "k-NN16", "PCA normals", "spanning-tree orientation", "initial segmentation",
-          "grid refinement (I=%d)", "patch segmentation (CC, D0/D1 projection, occupancy, residual loop)"]
+METRIC = "Mpoints/s patch-gen+image-formation, longdress_vox10, 1/2/4/8 GPU"
+HANDOFF = (2, 4, 5, 13, 14)  # products handed to the video codec: OM video, geometry D0/D1, padded attribute T0/T1
 
 
-def make_frames(count, scale, seed=0):
+def make_frames(count, scale, seed=0, distinct=8):
     import synth
-    frames = []
-    for f in range(count):
+    base = []
+    for f in range(min(count, distinct)):
         xyz, rgb = synth.figure(scale=scale, seed=seed, frame=f)
-        frames.append((np.ascontiguousarray(xyz), np.ascontiguousarray(rgb)))
-    return frames
+        base.append((np.ascontiguousarray(xyz), np.ascontiguousarray(rgb)))
+    return [base[f % len(base)] for f in range(count)]
 
 
 class ClockSampler(threading.Thread):
@@ -43,8 +50,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
-        self.proc = None
+        self.index, self.rows, self.proc = index, [], None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -54,23 +60,20 @@ class ClockSampler(threading.Thread):
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
-                if self.stop_flag:
-                    break
         except Exception:
             pass
 
     def finish(self):
-        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
+
+        def num(s):
+            return s.replace(".", "", 1).isdigit()
+
+        sm = [float(r[0]) for r in self.rows if r and num(r[0])]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and num(r[1])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for i, nme in enumerate(names):
-                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
-                    reasons.add(nme)
+        reasons = {nme for r in self.rows for i, nme in enumerate(names) if len(r) > 2 + i and r[2 + i].lower().startswith("active")}
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -83,7 +86,7 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# algorithmic bytes per launch, N = points of the frame; only single-kernel spans are listed
+# algorithmic bytes per launch of the single-kernel spans, N = points of the frame
 ALGO_BYTES = {
     "knn16": lambda n: 6 * n + 64 * n,
     "normals": lambda n: 64 * n + 6 * n + 24 * n,
@@ -91,23 +94,29 @@ ALGO_BYTES = {
 }
 
 
-def run_reference(args, frames, prm_for):
-    """--impl reference: the reference's own CPU code (oracle/_ref) on the host cores, one frame per process."""
+def config(args, npts, frames_per_rank, world):
+    return {"workload": "synthetic longdress-like figure(scale=%.3f), 10-bit, %.2f Mpts/frame, %d frames/step/GPU (%d distinct), CTC all-intra r3 "
+                        "(occupancyPrecision 4, I=%d refine iterations)" % (args.scale, npts / 1e6, frames_per_rank, min(frames_per_rank, 8), args.iterations),
+            "stages": "a1-a26: kd-tree, k-NN16, PCA normals, spanning-tree orientation, initial + grid-refined segmentation, patch segmentation, "
+                      "packing, occupancy/geometry images + dilation, generatePointCloud, colour transfer, attribute images, push-pull padding",
+            "excluded": "ply load, videoEncoder.compress x3, post-processing, bitstream (as in BASELINE.md §4)",
+            "frames_in_flight": frames_per_rank, "parallelism": "frames of a GOF sharded over %d GPU(s)" % world,
+            "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2"}
+
+
+def run_reference(args, frames, prm):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, TBB off) on the host cores, one frame per process."""
     import multiprocessing as mp
-    cores = max(1, min(len(frames), os.cpu_count() or 1))
+    cores = max(1, min(len(frames), os.cpu_count() or 1, args.ref_frames))
     work = frames[:cores]
     ctx = mp.get_context("fork")
 
-    def one(i, q):
+    def one(i):
         import bindings
-        ref = bindings.Reference()
-        t0 = time.perf_counter()
-        ref.segment_frame(work[i][0], work[i][1], prm_for(work[i][0]))
-        q.put(time.perf_counter() - t0)
+        bindings.Reference().encode_gof([work[i]], prm)
 
     def step():
-        q = ctx.Queue()
-        ps = [ctx.Process(target=one, args=(i, q)) for i in range(cores)]
+        ps = [ctx.Process(target=one, args=(i,)) for i in range(cores)]
         t0 = time.perf_counter()
         for p in ps:
             p.start()
@@ -121,13 +130,13 @@ def run_reference(args, frames, prm_for):
     pts = sum(len(f[0]) for f in work)
     sec = float(np.mean(times))
     val = pts / sec / 1e6
-    return {"metric": "Mpoints/s patch-gen+image-formation, longdress_vox10, 1/2/4/8 GPU", "value": val, "unit": "Mpoints/s",
-            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/f64", "data": "synthetic",
-            "config": {"workload": "figure(scale=%.2f) longdress-like 10-bit, %d frames/step, CTC all-intra r3 parameters" % (args.scale, cores),
-                       "stages": "PCCPatchSegmenter3::compute (a1-a11)", "note": "reference compiled from /root/reference, ENABLE_TBB off; one frame per process"},
+    cfg = config(args, float(np.mean([len(f[0]) for f in work])), cores, 1)
+    cfg["note"] = "reference TMC2 v24.0 compiled from /root/reference (ENABLE_TBB off, CTC --nbThread=1), one frame per host process"
+    return {"metric": METRIC, "value": val, "unit": "Mpoints/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps_ref,
+            "warmup": args.warmup_ref, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16/f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": "Mpoints/s", "cores": cores, "kind": "reference",
-                             "sample": "%d frame(s) of the workload, one per host core" % cores},
+                             "sample": "%d frame(s) of the workload per step, one per host core" % cores},
             "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -137,33 +146,24 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=4, help="frames per step")
-    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--frames", type=int, default=32, help="frames per step and GPU (a GOF is 32 frames)")
+    ap.add_argument("--scale", type=float, default=0.626, help="figure scale; 0.626 gives ~0.83 Mpts/frame like longdress_vox10")
     ap.add_argument("--iterations", type=int, default=50, help="iterationCountRefineSegmentation (longdress cfg: 50)")
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.steps_ref, args.warmup_ref = min(args.steps, 2), min(args.warmup, 1)
+    args.steps_ref, args.warmup_ref = 1, 0
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     import bindings
 
-    frames = make_frames(args.frames, args.scale, seed=rank)
-    # axis weights (PCCEncoder::calculateWeightNormal) come from frame 0 of the GOF
-    if args.impl == "reference":
-        weight = tuple(bindings.Reference().weight_normal(frames[0][0], 11))
-    else:
-        _p = bindings.Product(local)
-        weight = tuple(_p.weight_normal(frames[0][0], 11))
-        _p.close()
-
-    def prm_for(xyz):
-        return bindings.ctc_seg_params(bits=10, iterations=args.iterations, weight=weight)
-
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(run_reference(args, frames, prm_for)))
+            frames = make_frames(min(args.frames, args.ref_frames), args.scale, seed=0)
+            weight = tuple(bindings.Reference().weight_normal(frames[0][0], 11))
+            print(json.dumps(run_reference(args, frames, bindings.ctc_seg_params(bits=10, iterations=args.iterations, weight=weight))))
         return
 
     import torch
@@ -172,18 +172,38 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
+    frames = make_frames(args.frames, args.scale, seed=rank)
     prod = bindings.Product(local)
+    # axis weights come from frame 0 of the GOF (rank 0's first frame); every rank needs the same three doubles
+    w = torch.tensor(prod.weight_normal(frames[0][0], 11), dtype=torch.float64)
+    if dist is not None:
+        wd = w.cuda()
+        dist.broadcast(wd, 0)
+        w = wd.cpu()
+    prm = bindings.ctc_seg_params(bits=10, iterations=args.iterations, weight=tuple(float(x) for x in w))
     prod.profile(True)
-    prm = bindings.ctc_seg_params(bits=10, iterations=args.iterations, weight=weight)
     total_pts = sum(len(f[0]) for f in frames)
+    outbuf = {}
 
     def step():
-        spans = []
         t0 = time.perf_counter()
-        for xyz, rgb in frames:
-            prod.segment_frame(xyz, rgb, prm)
-            spans.append(prod.profile_read())
-        return time.perf_counter() - t0, spans
+        g = bindings.ProductGof(prod, frames, prm, 4)  # a1..a13
+        W, H, _ = g.dims(0)
+        if dist is not None:  # the one collective: common canvas size of the GOF
+            wh = torch.tensor([W, H], device="cuda", dtype=torch.int64)
+            dist.all_reduce(wh, op=dist.ReduceOp.MAX)
+            W, H = int(wh[0]), int(wh[1])
+        g.resume(W, H, 0)  # a16..a26
+        t1 = time.perf_counter()
+        nbytes = 0
+        for f in range(len(frames)):  # hand-off to the video codec: D2H of every frame it would receive
+            for what in HANDOFF:
+                outbuf[(f, what)] = g.fetch(f, what, outbuf.get((f, what)))
+                nbytes += outbuf[(f, what)].nbytes
+        t2 = time.perf_counter()
+        spans = prod.profile_read()
+        g.free()
+        return t1 - t0, t2 - t0, spans, nbytes
 
     def barrier():
         if dist is not None:
@@ -195,59 +215,61 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    wall, dev, launches_spans = [], [], []
+    t_begin = time.perf_counter()
+    call_t, e2e_t, dev_t, last_spans, d2h = 0.0, 0.0, 0.0, None, 0
     for _ in range(args.steps):
-        w, spans = step()
-        wall.append(w)
-        dev.append(sum(ms for fr in spans for nme, ms in fr if nme not in ("h2d", "d2h", "orient_walk")) / 1e3)
-        launches_spans = spans
+        c, e, spans, d2h = step()
+        call_t += c
+        e2e_t += e
+        comp = [(st, st + ms) for nme, ms, st in spans if st >= 0 and nme not in ("h2d", "d2h_patches")]
+        dev_t += (max(b for a, b in comp) - min(a for a, b in comp)) / 1e3 if comp else c
+        last_spans = spans
     barrier()
+    wall_total = time.perf_counter() - t_begin
     clocks = sampler.finish()
-    wall_t, dev_t = float(np.sum(wall)), float(np.sum(dev))
     if dist is not None:
-        t = torch.tensor([wall_t, dev_t], device="cuda", dtype=torch.float64)
+        t = torch.tensor([call_t, e2e_t, dev_t, wall_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall_t, dev_t = float(t[0]), float(t[1])
+        call_t, e2e_t, dev_t, wall_total = (float(x) for x in t)
     if rank != 0:
         return
     pts_all = total_pts * world * args.steps
-    # dominant span of the last step, averaged over its frames
     agg = {}
-    for fr in launches_spans:
-        for nme, ms in fr:
-            agg.setdefault(nme, []).append(ms)
+    for nme, ms, st in last_spans:
+        agg.setdefault(nme, []).append(ms)
     mean_ms = {k: float(np.mean(v)) for k, v in agg.items()}
-    share = {k: v / max(1e-9, sum(m for kk, m in mean_ms.items() if kk not in ("orient_walk",))) for k, v in mean_ms.items()}
     dom = max((k for k in mean_ms if k in ALGO_BYTES), key=lambda k: mean_ms[k])
     peak, how = measured_peak()
     npts = float(np.mean([len(f[0]) for f in frames]))
     ach = ALGO_BYTES[dom](npts) / (mean_ms[dom] * 1e-3) / 1e9
     h2d = sum(f[0].nbytes + f[1].nbytes for f in frames)
     out = {
-        "metric": "Mpoints/s patch-gen+image-formation, longdress_vox10, 1/2/4/8 GPU",
-        "value": pts_all / dev_t / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": wall_t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int16/f64", "data": "synthetic",
-        "config": {"workload": "figure(scale=%.2f) longdress-like 10-bit, %d frames/step (~%.2f Mpts/frame), CTC all-intra r3 parameters, I=%d"
-                               % (args.scale, args.frames, npts / 1e6, args.iterations),
-                   "stages": "a1-a11: " + "; ".join(STAGES) % args.iterations,
-                   "not_yet_in_timed_region": "a13-a26 packing, image formation, generatePointCloud, colour transfer, padding",
-                   "l2": "inputs (>126 MB of per-frame working set) exceed L2; every frame is uploaded afresh"},
-        "e2e": {"value": pts_all / wall_t / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": None},
+        "metric": METRIC, "value": pts_all / dev_t / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16/f64", "data": "synthetic", "config": config(args, npts, args.frames, world),
+        "e2e": {"value": pts_all / e2e_t / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": None,
         "stage_ms_per_frame": {k: round(v, 3) for k, v in sorted(mean_ms.items(), key=lambda kv: -kv[1])},
-        "stage_share": {k: round(v, 3) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "peak_source": how, "algorithmic_bytes_per_launch": ALGO_BYTES[dom](npts)},
+                     "peak_source": how, "algorithmic_bytes_per_launch": ALGO_BYTES[dom](npts),
+                     "note": "single-warp sequential walk: latency-bound by construction; frames run concurrently to fill the machine"},
         "clocks": clocks,
     }
+    counts_path = os.path.join(ROOT, "profiles", "launch_counts.json")
+    if os.path.exists(counts_path):
+        with open(counts_path) as f:
+            lc = json.load(f)
+        out["gpu_launches"] = int(lc.get("launches_per_frame", 0) * args.frames * args.steps)
+        out["gpu_launches_source"] = lc.get("source")
+        if lc.get("traffic_bytes_per_launch", {}).get(dom):
+            out["roofline"]["traffic"] = lc["traffic_bytes_per_launch"][dom]
     if not args.no_cpu_baseline and os.path.exists(bindings.REF_SO):
         ref = bindings.Reference()
         t0 = time.perf_counter()
-        ref.segment_frame(frames[0][0], frames[0][1], prm)
+        ref.encode_gof([frames[0]], prm)
         sec = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": len(frames[0][0]) / sec / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "reference",
-                               "sample": "1 frame of the workload (%.2f Mpts), reference PCCPatchSegmenter3 single thread (CTC --nbThread=1)" % (len(frames[0][0]) / 1e6)}
+                               "sample": "1 frame of the workload (%.2f Mpts) through the reference's own stages, single thread (CTC --nbThread=1)" % (len(frames[0][0]) / 1e6)}
     print(json.dumps(out))
 
 

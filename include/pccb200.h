@@ -86,9 +86,10 @@ const char* pccb200_last_error( const pccb200_ctx* ctx );
 const char* pccb200_version( void );
 
 /* Per-stage device timing (CUDA events on the launching stream). While enabled, every entry point appends one
- * (name, milliseconds) record per stage; read returns and clears them. names: capacity x 32 chars. */
+ * (name, milliseconds) record per stage and frame; read returns and clears them. names: capacity x 32 chars; start_ms
+ * (may be NULL) = start of the span relative to the beginning of the GOF call (-1 for the single-frame entry points). */
 int pccb200_profile_enable( pccb200_ctx* ctx, int on );
-int pccb200_profile_read( pccb200_ctx* ctx, char* names, float* ms, int capacity, int* count );
+int pccb200_profile_read( pccb200_ctx* ctx, char* names, float* ms, float* start_ms, int capacity, int* count );
 
 /* ---- stage-level entry points -------------------------------------------------------------------------
  * Each replaces one public reference class used on its own by the tools (PccAppNormalGenerator uses PCCKdTree +
@@ -142,6 +143,10 @@ void   pccb200_patches_free( pccb200_patchlist* pl );
 typedef struct pccb200_gof pccb200_gof;
 int  pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
                          const pccb200_seg_params* params, int occupancy_precision, int stop_after, pccb200_gof** out );
+/* Multi-GPU (frames of one GOF sharded over ranks): call pccb200_encode_gof with stop_after = 1 on every rank, all-reduce
+ * (MAX) the canvas size from pccb200_gof_dims — the one cross-frame reduction of the all-intra path
+ * (PCCEncoder::resizeGeometryVideo, PCCEncoder.cpp:5546-5591) — then resume the remaining stages on that canvas. */
+int  pccb200_gof_resume( pccb200_gof* gof, size_t width, size_t height, int stop_after );
 void pccb200_gof_free( pccb200_gof* gof );
 /* canvas size (identical for all frames of the GOF) and number of reconstructed points of frame f */
 int  pccb200_gof_dims( const pccb200_gof* gof, int f, size_t* width, size_t* height, size_t* rec_points );

@@ -50,7 +50,7 @@ int pccb200_profile_enable( pccb200_ctx* ctx, int on ) {
   return PCCB200_OK;
 }
 
-int pccb200_profile_read( pccb200_ctx* ctx, char* names, float* ms, int capacity, int* count ) {
+int pccb200_profile_read( pccb200_ctx* ctx, char* names, float* ms, float* start_ms, int capacity, int* count ) {
   if ( !ctx || !count ) return PCCB200_ERR_BAD_ARG;
   const int n = int( ctx->prof.results.size() );
   *count      = n;
@@ -58,6 +58,7 @@ int pccb200_profile_read( pccb200_ctx* ctx, char* names, float* ms, int capacity
     for ( int i = 0; i < n && i < capacity; ++i ) {
       snprintf( names + 32 * i, 32, "%s", ctx->prof.results[i].first );
       ms[i] = ctx->prof.results[i].second;
+      if ( start_ms ) start_ms[i] = ctx->prof.results[i].start;
     }
     ctx->prof.results.clear();
   }

@@ -104,7 +104,13 @@ struct Profiler {
   };
   bool              enabled = false;
   std::vector<Span> spans;
-  std::vector<std::pair<const char*, float>> results;  // filled by collect()
+  struct Result {
+    const char* first;   // stage name
+    float       second;  // duration (ms)
+    float       start;   // start offset (ms) from the origin event, or -1
+  };
+  std::vector<Result> results;  // filled by collect()
+  cudaEvent_t         origin = nullptr;  // optional common time origin (recorded by the owner)
   void begin( const char* name, cudaStream_t s ) {
     if ( !enabled ) return;
     Span sp{ name, nullptr, nullptr };
@@ -127,9 +133,10 @@ struct Profiler {
     if ( !enabled ) return;
     cudaStreamSynchronize( s );
     for ( size_t i = 0; i < spans.size(); ++i ) {
-      float ms = 0;
+      float ms = 0, st = -1.f;
       if ( closed[i] ) cudaEventElapsedTime( &ms, spans[i].a, spans[i].b );
-      results.emplace_back( spans[i].name, ms );
+      if ( origin && cudaEventElapsedTime( &st, origin, spans[i].a ) != cudaSuccess ) st = -1.f, cudaGetLastError();
+      results.push_back( Result{ spans[i].name, ms, st } );
       cudaEventDestroy( spans[i].a ), cudaEventDestroy( spans[i].b );
     }
     spans.clear(), closed.clear();

@@ -177,48 +177,12 @@ __global__ void kUnpackRgb( const uchar4* __restrict__ in, int n, uint8_t* __res
   if ( i < n ) out[3 * size_t( i )] = in[i].x, out[3 * size_t( i ) + 1] = in[i].y, out[3 * size_t( i ) + 2] = in[i].z;
 }
 
-}  // namespace
 
-extern "C" {
-
-int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
-                        const pccb200_seg_params* prm, int occupancyPrecision, int stopAfter, pccb200_gof** out ) {
-  if ( !ctx || !out || nframes < 0 || ( nframes > 0 && ( !xyz || !rgb || !n ) ) || !prm ) return PCCB200_ERR_BAD_ARG;
-  if ( prm->nn_normal_estimation != 16 || prm->max_nn_count_patch_seg != 16 || prm->geometry_bitdepth_3d > 12 || prm->occupancy_resolution != 16 ||
-       ( prm->normal_orientation != 0 && prm->normal_orientation != 1 ) || occupancyPrecision < 1 || 16 % occupancyPrecision != 0 ||
-       prm->map_count_minus1 != 1 )
-    return PCCB200_ERR_UNSUPPORTED;
-  *out = nullptr;
-  return guarded( ctx, [&]() -> int {
-    pccb200_gof* g = new pccb200_gof();
-    g->ctx = ctx, g->nframes = nframes, g->occPrec = occupancyPrecision, g->prm = *prm;
-    while ( int( ctx->framePool.size() ) < nframes ) {
-      ctx->framePool.emplace_back( new FrameState() );
-      PCC_CUDA( cudaStreamCreateWithFlags( &ctx->framePool.back()->stream, cudaStreamNonBlocking ) );
-    }
-    for ( int f = 0; f < nframes; ++f ) {
-      FrameState* fs = ctx->framePool[f].get();
-      fs->hXyz = xyz[f], fs->hRgb = rgb[f], fs->n = n[f], fs->status = 0, fs->error.clear();
-      fs->prof.enabled = ctx->prof.enabled;
-      g->frames.push_back( fs );
-    }
-    const int minW = prm->geometry_bitdepth_3d > 11 ? 2560 : 1280, minH = 1280;  // minimumImageWidth/Height (cfg/sequence/*_vox11.cfg: 2560)
-    int       rc   = forEachFrame( g, [&]( FrameState& fs, int ) {
-      segmentFrame( fs, g->prm );
-      packFrame( fs, g->prm, minW, minH, 2, 1.0 );
-    } );
-    if ( rc != PCCB200_OK ) {
-      delete g;
-      return rc;
-    }
-    // a14: one canvas size per GOF (PCCEncoder::resizeTileGeometryVideo + resizeGeometryVideo, PCCEncoder.cpp:5546-5634)
-    size_t W = minW, H = minH;
-    for ( auto* fs : g->frames ) H = std::max( H, size_t( fs->heightPx ) );
-    g->W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), g->H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
-    g->stage = 1;
-    const int Wi = int( g->W ), Hi = int( g->H );
-    if ( stopAfter != 1 ) {
-      rc = forEachFrame( g, [&]( FrameState& fs, int ) {
+// a16..a26 on a fixed canvas (g->W x g->H): occupancy + geometry images, reconstruction, colour transfer, attribute images
+int runCanvasStages( pccb200_gof* g, int stopAfter ) {
+  const int Wi = int( g->W ), Hi = int( g->H );
+  int       rc = PCCB200_OK;
+  rc = forEachFrame( g, [&]( FrameState& fs, int ) {
         cudaStream_t s = fs.stream;
         {
           ProfScope t( &fs.prof, "images", s );
@@ -248,11 +212,70 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
           formAttributeImages( fs.rc.pointToPixel, fs.recRgb, R, fs.im.om, Wi, Hi, g->occPrec, fs.attr, s );
         }
       } );
+  if ( rc != PCCB200_OK ) return rc;
+  g->stage = stopAfter == 2 ? 2 : ( stopAfter == 3 ? 3 : 4 );
+  return PCCB200_OK;
+}
+
+void collectProfiles( pccb200_gof* g ) {
+  for ( auto* fs : g->frames ) {
+    fs->prof.collect( fs->stream );
+    for ( auto& r : fs->prof.results ) g->ctx->prof.results.push_back( r );
+    fs->prof.results.clear();
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                        const pccb200_seg_params* prm, int occupancyPrecision, int stopAfter, pccb200_gof** out ) {
+  if ( !ctx || !out || nframes < 0 || ( nframes > 0 && ( !xyz || !rgb || !n ) ) || !prm ) return PCCB200_ERR_BAD_ARG;
+  if ( prm->nn_normal_estimation != 16 || prm->max_nn_count_patch_seg != 16 || prm->geometry_bitdepth_3d > 12 || prm->occupancy_resolution != 16 ||
+       ( prm->normal_orientation != 0 && prm->normal_orientation != 1 ) || occupancyPrecision < 1 || 16 % occupancyPrecision != 0 ||
+       prm->map_count_minus1 != 1 )
+    return PCCB200_ERR_UNSUPPORTED;
+  *out = nullptr;
+  return guarded( ctx, [&]() -> int {
+    pccb200_gof* g = new pccb200_gof();
+    g->ctx = ctx, g->nframes = nframes, g->occPrec = occupancyPrecision, g->prm = *prm;
+    while ( int( ctx->framePool.size() ) < nframes ) {
+      ctx->framePool.emplace_back( new FrameState() );
+      PCC_CUDA( cudaStreamCreateWithFlags( &ctx->framePool.back()->stream, cudaStreamNonBlocking ) );
+    }
+    if ( ctx->prof.enabled ) {  // common time origin of all frame streams
+      if ( !ctx->prof.origin ) PCC_CUDA( cudaEventCreate( &ctx->prof.origin ) );
+      PCC_CUDA( cudaEventRecord( ctx->prof.origin, ctx->stream ) );
+      PCC_CUDA( cudaEventSynchronize( ctx->prof.origin ) );
+    }
+    for ( int f = 0; f < nframes; ++f ) {
+      FrameState* fs = ctx->framePool[f].get();
+      fs->hXyz = xyz[f], fs->hRgb = rgb[f], fs->n = n[f], fs->status = 0, fs->error.clear();
+      fs->prof.enabled = ctx->prof.enabled;
+      fs->prof.origin  = ctx->prof.enabled ? ctx->prof.origin : nullptr;
+      g->frames.push_back( fs );
+    }
+    const int minW = prm->geometry_bitdepth_3d > 11 ? 2560 : 1280, minH = 1280;  // minimumImageWidth/Height (cfg/sequence/*_vox11.cfg: 2560)
+    int       rc   = forEachFrame( g, [&]( FrameState& fs, int ) {
+      segmentFrame( fs, g->prm );
+      packFrame( fs, g->prm, minW, minH, 2, 1.0 );
+    } );
+    if ( rc != PCCB200_OK ) {
+      delete g;
+      return rc;
+    }
+    // a14: one canvas size per GOF (PCCEncoder::resizeTileGeometryVideo + resizeGeometryVideo, PCCEncoder.cpp:5546-5634)
+    size_t W = minW, H = minH;
+    for ( auto* fs : g->frames ) H = std::max( H, size_t( fs->heightPx ) );
+    g->W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), g->H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
+    g->stage = 1;
+    if ( stopAfter != 1 ) {
+      rc = runCanvasStages( g, stopAfter );
       if ( rc != PCCB200_OK ) {
         delete g;
         return rc;
       }
-      g->stage = stopAfter == 2 ? 2 : ( stopAfter == 3 ? 3 : 4 );
     }
     // host copies of the packed patch lists (KBs of metadata + the per-patch maps downstream reference code reads)
     g->lists.resize( nframes );
@@ -278,17 +301,25 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
         dOff += px, oOff += nb;
       }
     } );
-    for ( auto* fs : g->frames ) {
-      fs->prof.collect( fs->stream );
-      for ( auto& r : fs->prof.results ) ctx->prof.results.push_back( r );
-      fs->prof.results.clear();
-    }
+    collectProfiles( g );
     if ( rc != PCCB200_OK ) {
       delete g;
       return rc;
     }
     *out = g;
     return PCCB200_OK;
+  } );
+}
+
+int pccb200_gof_resume( pccb200_gof* g, size_t width, size_t height, int stopAfter ) {
+  if ( !g || stopAfter == 1 ) return PCCB200_ERR_BAD_ARG;
+  if ( g->stage != 1 ) return PCCB200_ERR_STATE;
+  if ( width < g->W || height < g->H || width % 64 || height % 64 ) return PCCB200_ERR_BAD_ARG;
+  return guarded( g->ctx, [&]() -> int {
+    g->W = width, g->H = height;
+    const int rc = runCanvasStages( g, stopAfter );
+    collectProfiles( g );
+    return rc;
   } );
 }
 

@@ -325,7 +325,7 @@ class Product:
         L.pccb200_patches_free.argtypes = [C.c_void_p]
         L.pccb200_weight_normal.argtypes = [C.c_void_p, c_i16p, C.c_size_t, C.c_int, C.c_double, c_f64p]
         L.pccb200_profile_enable.argtypes = [C.c_void_p, C.c_int]
-        L.pccb200_profile_read.argtypes = [C.c_void_p, C.c_char_p, c_f32p, C.c_int, C.POINTER(C.c_int)]
+        L.pccb200_profile_read.argtypes = [C.c_void_p, C.c_char_p, c_f32p, c_f32p, C.c_int, C.POINTER(C.c_int)]
         self.ctx = C.c_void_p()
         rc = L.pccb200_create(device, C.byref(self.ctx))
         if rc != 0:
@@ -386,14 +386,15 @@ class Product:
 
     def profile_read(self):
         """[(stage name, device milliseconds)] recorded since the last read"""
-        cap = 256
+        cap = 4096
         names = C.create_string_buffer(32 * cap)
         ms = np.zeros(cap, np.float32)
+        st = np.zeros(cap, np.float32)
         cnt = C.c_int(0)
-        self._check(self.lib.pccb200_profile_read(self.ctx, names, ptr(ms, c_f32p), cap, C.byref(cnt)))
+        self._check(self.lib.pccb200_profile_read(self.ctx, names, ptr(ms, c_f32p), ptr(st, c_f32p), cap, C.byref(cnt)))
         out = []
         for i in range(min(cnt.value, cap)):
-            out.append((names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), float(ms[i])))
+            out.append((names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), float(ms[i]), float(st[i])))
         return out
 
     def weight_normal(self, xyz, bits, min_w=0.6):
@@ -587,3 +588,42 @@ def _product_encode_gof(self, frames, params, occupancy_precision=4, stop_after=
 
 
 Product.encode_gof = _product_encode_gof
+
+
+class ProductGof:
+    """staged use of the GOF entry points (pack -> [all-reduce canvas] -> resume -> fetch hand-off products)"""
+
+    def __init__(self, product, frames, params, occupancy_precision=4):
+        self.p, L = product, product.lib
+        _product_encode_gof.__doc__  # (signatures are declared there)
+        L.pccb200_encode_gof.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_i16p), C.POINTER(c_u8p), C.POINTER(C.c_size_t), C.POINTER(SegParams),
+                                         C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.pccb200_gof_free.argtypes = [C.c_void_p]
+        L.pccb200_gof_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.pccb200_gof_get.restype = C.c_size_t
+        L.pccb200_gof_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pccb200_gof_resume.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
+        self.n, self._xs, self._cs, xp, cp, ns = _frames_args(frames)
+        self.h = C.c_void_p()
+        product._check(L.pccb200_encode_gof(product.ctx, self.n, xp, cp, ns, C.byref(params), occupancy_precision, 1, C.byref(self.h)))
+
+    def dims(self, f=0):
+        w, hh, r = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self.p.lib.pccb200_gof_dims(self.h, f, C.byref(w), C.byref(hh), C.byref(r))
+        return w.value, hh.value, r.value
+
+    def resume(self, width, height, stop_after=0):
+        self.p._check(self.p.lib.pccb200_gof_resume(self.h, width, height, stop_after))
+
+    def fetch(self, f, what, out=None):
+        cnt = self.p.lib.pccb200_gof_get(self.h, f, what, None)
+        if out is None or out.size != cnt:
+            out = np.empty(cnt, GOF_DTYPES[what])
+        if cnt:
+            self.p.lib.pccb200_gof_get(self.h, f, what, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def free(self):
+        if self.h:
+            self.p.lib.pccb200_gof_free(self.h)
+            self.h = C.c_void_p()
