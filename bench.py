@@ -27,6 +27,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per frame stream (before CUDA initialises)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -100,7 +101,7 @@ def config(args, npts, frames_per_rank, world):
             "stages": "a1-a26: kd-tree, k-NN16, PCA normals, spanning-tree orientation, initial + grid-refined segmentation, patch segmentation, "
                       "packing, occupancy/geometry images + dilation, generatePointCloud, colour transfer, attribute images, push-pull padding",
             "excluded": "ply load, videoEncoder.compress x3, post-processing, bitstream (as in BASELINE.md §4)",
-            "frames_in_flight": frames_per_rank, "parallelism": "frames of a GOF sharded over %d GPU(s)" % world,
+            "frames_in_flight": frames_per_rank, "host_cores": os.cpu_count(), "parallelism": "frames of a GOF sharded over %d GPU(s)" % world,
             "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2"}
 
 

@@ -1,4 +1,6 @@
 // api.cu — the C ABI (include/pccb200.h). Host-side orchestration only; all point/pixel work is in kernels.
+#include <stdlib.h>
+
 #include <mutex>
 #include <algorithm>
 #include <new>
@@ -16,6 +18,8 @@ const char* pccb200_version( void ) { return "pccb200 0.1 (sm_100a)"; }
 int pccb200_create( int device, pccb200_ctx** out ) {
   if ( !out ) return PCCB200_ERR_BAD_ARG;
   *out      = nullptr;
+  // one hardware work queue per frame stream (must be set before the CUDA context exists; harmless otherwise)
+  setenv( "CUDA_DEVICE_MAX_CONNECTIONS", "32", 0 );
   int count = 0;
   if ( cudaGetDeviceCount( &count ) != cudaSuccess || count <= 0 || device < 0 || device >= count ) {
     cudaGetLastError();

@@ -17,6 +17,8 @@
 // Frames of a GOF run this stage concurrently on separate streams (one resident warp each).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <mutex>
+
 #include "stages.cuh"
 
 namespace pccb200 {
@@ -303,12 +305,21 @@ void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, i
   a.L0 = sc.L0, a.best = sc.best, a.flip = sc.flip;
   const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 ) * 8;
   if ( smemBytes > 200 * 1024 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
-  PCC_CUDA( cudaFuncSetAttribute( kWalk, cudaFuncAttributeMaxDynamicSharedMemorySize, int( smemBytes ) ) );
+  {  // the limit is a per-function global: raise it once to the maximum any frame may need (frames run on concurrent host threads)
+    static std::once_flag once;
+    cudaError_t           err = cudaSuccess;
+    std::call_once( once, [&]() { err = cudaFuncSetAttribute( kWalk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 ); } );
+    PCC_CUDA( err );
+  }
   {
     ProfScope t( sc.prof, "orient_walk", s );
     kWalk<<<1, 32, smemBytes, s>>>( a );
     PCC_LAUNCH_CHECK();
   }
+  // The walk runs for seconds on one warp. Nothing that depends on it is enqueued until it has finished: a dependent
+  // launch waiting at the head of a hardware queue would stall unrelated kernels of other frames' streams that share the
+  // queue (CUDA_DEVICE_MAX_CONNECTIONS queues for all streams). The per-frame host thread simply waits here.
+  PCC_CUDA( cudaStreamSynchronize( s ) );
   kApplyFlip<<<divUp( n, 256 ), 256, 0, s>>>( normals, sc.flip, pts, int( n ), sc.counter );
   kNegateIfMajority<<<divUp( 3 * n, 256 ), 256, 0, s>>>( normals, int( n ), sc.counter );
   PCC_LAUNCH_CHECK();
