@@ -147,7 +147,24 @@ int  pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xy
  * (MAX) the canvas size from pccb200_gof_dims — the one cross-frame reduction of the all-intra path
  * (PCCEncoder::resizeGeometryVideo, PCCEncoder.cpp:5546-5591) — then resume the remaining stages on that canvas. */
 int  pccb200_gof_resume( pccb200_gof* gof, size_t width, size_t height, int stop_after );
+/* Lossy geometry codec: run pccb200_encode_gof / pccb200_gof_resume with stop_after = 2, hand GOF_OM_VIDEO / GOF_GEO0 / GOF_GEO1 to
+ * the codec, give the DECODED luma planes back (any pointer may be NULL = keep the source), then pccb200_gof_resume(gof, W, H, 0)
+ * reconstructs from them exactly as PCCEncoder::encode does after videoEncoder.compress replaced `video` by the reconstruction
+ * (PCCVideoEncoder.cpp:403-416, PCCEncoder.cpp:168, 319-334). */
+int  pccb200_gof_set_decoded( pccb200_gof* gof, int f, const uint8_t* occ_video, const uint16_t* geo0, const uint16_t* geo1 );
 void pccb200_gof_free( pccb200_gof* gof );
+
+/* PCCCodec::generatePointCloud (PccLibCommon/source/PCCCodec.cpp:519-980) as PCCDecoder::decode calls it
+ * (PccLibDecoder/source/PCCDecoder.cpp:334-351), CTC reconstruction options (two maps, absolute D1, duplicate removal, no EOM/PLR/
+ * raw patches): `patches` in atlas order with the fields the decoder rebuilds from the syntax (u0, v0, orientation, size_u0,
+ * size_v0, u1, v1, d1, view_id; PCCDecoder.cpp:900-1040), decoded occupancy video luma ((W/p)*(H/p) uint8), decoded geometry luma
+ * D0/D1 (W*H uint16). Outputs (each may be NULL) hold up to `capacity` points: positions (n x 3 int16), pointToPixel (n x 3
+ * uint32: x, y, map), partition (patch index) and boundary point type. *rec_points receives the true count; when it exceeds
+ * capacity and an output was requested the call returns PCCB200_ERR_CAPACITY (call once with capacity 0 / NULL outputs to size). */
+int  pccb200_generate_point_cloud( pccb200_ctx* ctx, const pccb200_patch* patches, int num_patches, const uint8_t* occ_video,
+                                   const uint16_t* geo0, const uint16_t* geo1, size_t width, size_t height, int occupancy_precision,
+                                   size_t capacity, int16_t* xyz, uint32_t* point_to_pixel, uint32_t* partition, uint16_t* boundary,
+                                   size_t* rec_points );
 /* canvas size (identical for all frames of the GOF) and number of reconstructed points of frame f */
 int  pccb200_gof_dims( const pccb200_gof* gof, int f, size_t* width, size_t* height, size_t* rec_points );
 /* patches of frame f in PACKED order (the order of tile.getPatches() after packFlexible) with u0/v0/orientation filled;

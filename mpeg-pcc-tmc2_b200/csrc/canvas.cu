@@ -495,6 +495,18 @@ void formOccupancyAndGeometry( const CanvasPatch* dPatches, int numPatches, int 
   PCC_LAUNCH_CHECK();
 }
 
+// a18 alone: block-to-patch from a (decoded) occupancy video
+void blockToPatchFromVideo( const CanvasPatch* dPatches, int numPatches, int maxPatchBlocks, int occRes, int prec, int W, int H, const uint8_t* om,
+                            uint32_t* blockToPatch, cudaStream_t s ) {
+  const size_t blocks = size_t( W / occRes ) * ( H / occRes );
+  PCC_CUDA( cudaMemsetAsync( blockToPatch, 0, blocks * 4, s ) );
+  if ( numPatches ) {
+    const dim3 g( std::max( 1, divUp( maxPatchBlocks, 128 ) ), numPatches );
+    kBlockToPatch<<<g, 128, 0, s>>>( dPatches, om, occRes, prec, W, H, blockToPatch );
+    PCC_LAUNCH_CHECK();
+  }
+}
+
 size_t reconstructPoints( const CanvasPatch* dPatches, const long long* dElemBase, int numPatches, long long totalElems, int occRes, int prec, int W,
                           int H, const uint8_t* om, const uint32_t* blockToPatch, const uint16_t* geo0, const uint16_t* geo1, ReconScratch& rc,
                           cudaStream_t s ) {

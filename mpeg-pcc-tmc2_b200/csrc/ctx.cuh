@@ -35,6 +35,7 @@ struct FrameState {
   ColorScratch               color;
   AttrImages                 attr;
   Profiler                   prof;
+  bool                       decodedSet = false;  // the caller replaced om/geo0/geo1 by decoded planes
   int                        status = 0;
   std::string                error;
   ~FrameState() {

@@ -182,17 +182,24 @@ __global__ void kUnpackRgb( const uchar4* __restrict__ in, int n, uint8_t* __res
 int runCanvasStages( pccb200_gof* g, int stopAfter ) {
   const int Wi = int( g->W ), Hi = int( g->H );
   int       rc = PCCB200_OK;
+  const bool haveImages = g->stage >= 2;
   rc = forEachFrame( g, [&]( FrameState& fs, int ) {
         cudaStream_t s = fs.stream;
-        {
-          ProfScope t( &fs.prof, "images", s );
-          formOccupancyAndGeometry( fs.dPatches, int( fs.packed.size() ), fs.maxPatchPixels, fs.maxPatchBlocks, fs.seg.depth, g->prm.occupancy_resolution,
-                                    g->occPrec, Wi, Hi, fs.im, s );
+        if ( !haveImages ) {
+          {
+            ProfScope t( &fs.prof, "images", s );
+            formOccupancyAndGeometry( fs.dPatches, int( fs.packed.size() ), fs.maxPatchPixels, fs.maxPatchBlocks, fs.seg.depth, g->prm.occupancy_resolution,
+                                      g->occPrec, Wi, Hi, fs.im, s );
+          }
+          int err = 0;
+          PCC_CUDA( cudaMemcpyAsync( &err, fs.im.error, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+          PCC_CUDA( cudaStreamSynchronize( s ) );
+          if ( err ) throw std::runtime_error( "patch2Canvas out of the canvas" );
+        } else if ( fs.decodedSet ) {
+          // decoded occupancy video: a18 again (generateBlockToPatchFromOccupancyMapVideo runs on the decoded frame, :168)
+          blockToPatchFromVideo( fs.dPatches, int( fs.packed.size() ), fs.maxPatchBlocks, g->prm.occupancy_resolution, g->occPrec, Wi, Hi, fs.im.om,
+                                 fs.im.blockToPatch, s );
         }
-        int err = 0;
-        PCC_CUDA( cudaMemcpyAsync( &err, fs.im.error, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
-        PCC_CUDA( cudaStreamSynchronize( s ) );
-        if ( err ) throw std::runtime_error( "patch2Canvas out of the canvas" );
         if ( stopAfter == 2 ) return;
         // the occupancy and geometry videos are coded losslessly / passed through here: decoded == source
         {
@@ -253,6 +260,7 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
       FrameState* fs = ctx->framePool[f].get();
       fs->hXyz = xyz[f], fs->hRgb = rgb[f], fs->n = n[f], fs->status = 0, fs->error.clear();
       fs->prof.enabled = ctx->prof.enabled;
+      fs->decodedSet   = false;
       fs->prof.origin  = ctx->prof.enabled ? ctx->prof.origin : nullptr;
       g->frames.push_back( fs );
     }
@@ -313,13 +321,88 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
 
 int pccb200_gof_resume( pccb200_gof* g, size_t width, size_t height, int stopAfter ) {
   if ( !g || stopAfter == 1 ) return PCCB200_ERR_BAD_ARG;
-  if ( g->stage != 1 ) return PCCB200_ERR_STATE;
+  if ( g->stage != 1 && g->stage != 2 ) return PCCB200_ERR_STATE;
   if ( width < g->W || height < g->H || width % 64 || height % 64 ) return PCCB200_ERR_BAD_ARG;
+  if ( g->stage == 2 && ( width != g->W || height != g->H || stopAfter == 2 ) ) return PCCB200_ERR_BAD_ARG;
   return guarded( g->ctx, [&]() -> int {
     g->W = width, g->H = height;
     const int rc = runCanvasStages( g, stopAfter );
     collectProfiles( g );
     return rc;
+  } );
+}
+
+int pccb200_gof_set_decoded( pccb200_gof* g, int f, const uint8_t* occVideo, const uint16_t* geo0, const uint16_t* geo1 ) {
+  if ( !g || f < 0 || f >= g->nframes ) return PCCB200_ERR_BAD_ARG;
+  if ( g->stage != 2 ) return PCCB200_ERR_STATE;
+  return guarded( g->ctx, [&]() -> int {
+    FrameState&  fs = *g->frames[f];
+    const size_t Q = g->W * g->H, cells = ( g->W / g->occPrec ) * ( g->H / g->occPrec );
+    if ( occVideo ) PCC_CUDA( cudaMemcpyAsync( fs.im.om, occVideo, cells, cudaMemcpyHostToDevice, fs.stream ) );
+    if ( geo0 ) PCC_CUDA( cudaMemcpyAsync( fs.im.geo0, geo0, Q * 2, cudaMemcpyHostToDevice, fs.stream ) );
+    if ( geo1 ) PCC_CUDA( cudaMemcpyAsync( fs.im.geo1, geo1, Q * 2, cudaMemcpyHostToDevice, fs.stream ) );
+    PCC_CUDA( cudaStreamSynchronize( fs.stream ) );
+    fs.decodedSet = fs.decodedSet || occVideo != nullptr;
+    return PCCB200_OK;
+  } );
+}
+
+// PCCCodec::generatePointCloud as the decoder calls it (PccLibDecoder/source/PCCDecoder.cpp:334-351): patches rebuilt from the
+// atlas syntax, decoded occupancy + geometry frames in, reconstructed cloud out.
+int pccb200_generate_point_cloud( pccb200_ctx* ctx, const pccb200_patch* patches, int numPatches, const uint8_t* occVideo, const uint16_t* geo0,
+                                  const uint16_t* geo1, size_t width, size_t height, int occupancyPrecision, size_t capacity, int16_t* xyz,
+                                  uint32_t* pointToPixel, uint32_t* partition, uint16_t* boundary, size_t* recPoints ) {
+  if ( !ctx || numPatches < 0 || ( numPatches && !patches ) || !occVideo || !geo0 || !geo1 || !recPoints || width % 16 || height % 16 ||
+       occupancyPrecision < 1 || 16 % occupancyPrecision )
+    return PCCB200_ERR_BAD_ARG;
+  return guarded( ctx, [&]() -> int {
+    if ( ctx->framePool.empty() ) {
+      ctx->framePool.emplace_back( new FrameState() );
+      PCC_CUDA( cudaStreamCreateWithFlags( &ctx->framePool.back()->stream, cudaStreamNonBlocking ) );
+    }
+    FrameState&  fs = *ctx->framePool[0];
+    cudaStream_t s  = fs.stream;
+    const int    W = int( width ), H = int( height ), occRes = 16, P = numPatches;
+    const size_t Q = width * height, cells = ( width / occupancyPrecision ) * ( height / occupancyPrecision ), blocks = ( width / 16 ) * ( height / 16 );
+    std::vector<CanvasPatch> cp( P );
+    std::vector<long long>   base( P + 1 );
+    long long                total = 0;
+    int                      maxBlocks = 1;
+    for ( int i = 0; i < P; ++i ) {
+      const pccb200_patch& m = patches[i];
+      if ( m.view_id < 0 || m.view_id > 5 || ( m.orientation != 0 && m.orientation != 1 ) ) return PCCB200_ERR_UNSUPPORTED;
+      CanvasPatch& c = cp[i];
+      c.viewId = m.view_id, c.u1 = m.u1, c.v1 = m.v1, c.d1 = m.d1, c.sizeU = m.size_u, c.sizeV = m.size_v, c.sizeU0 = m.size_u0, c.sizeV0 = m.size_v0;
+      c.u0 = m.u0, c.v0 = m.v0, c.orientation = m.orientation, c.pad = 0, c.depthOff = c.occOff = 0;
+      base[i] = total;
+      total += (long long)m.size_u0 * m.size_v0 * occRes * occRes;
+      maxBlocks = std::max( maxBlocks, m.size_u0 * m.size_v0 );
+    }
+    base[P] = total;
+    fs.dPatches.reserve( P + 1 ), fs.elemBase.reserve( P + 2 );
+    fs.im.om.reserve( cells ), fs.im.geo0.reserve( Q ), fs.im.geo1.reserve( Q ), fs.im.blockToPatch.reserve( blocks );
+    if ( P ) PCC_CUDA( cudaMemcpyAsync( fs.dPatches, cp.data(), P * sizeof( CanvasPatch ), cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( fs.elemBase, base.data(), ( P + 1 ) * sizeof( long long ), cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( fs.im.om, occVideo, cells, cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( fs.im.geo0, geo0, Q * 2, cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( fs.im.geo1, geo1, Q * 2, cudaMemcpyHostToDevice, s ) );
+    blockToPatchFromVideo( fs.dPatches, P, maxBlocks, occRes, occupancyPrecision, W, H, fs.im.om, fs.im.blockToPatch, s );
+    const size_t R = reconstructPoints( fs.dPatches, fs.elemBase, P, total, occRes, occupancyPrecision, W, H, fs.im.om, fs.im.blockToPatch, fs.im.geo0,
+                                        fs.im.geo1, fs.rc, s );
+    *recPoints = R;
+    if ( R > capacity ) return ( xyz || pointToPixel || partition || boundary ) ? PCCB200_ERR_CAPACITY : PCCB200_OK;
+    if ( R ) {
+      if ( xyz ) {
+        fs.xyzRaw.reserve( 3 * R );
+        kUnpackXyz<<<divUp( R, 256 ), 256, 0, s>>>( fs.rc.recXyz, int( R ), fs.xyzRaw );
+        PCC_CUDA( cudaMemcpyAsync( xyz, fs.xyzRaw, 3 * R * 2, cudaMemcpyDeviceToHost, s ) );
+      }
+      if ( pointToPixel ) PCC_CUDA( cudaMemcpyAsync( pointToPixel, fs.rc.pointToPixel, 3 * R * 4, cudaMemcpyDeviceToHost, s ) );
+      if ( partition ) PCC_CUDA( cudaMemcpyAsync( partition, fs.rc.recPartition, R * 4, cudaMemcpyDeviceToHost, s ) );
+      if ( boundary ) PCC_CUDA( cudaMemcpyAsync( boundary, fs.rc.boundary, R * 2, cudaMemcpyDeviceToHost, s ) );
+    }
+    PCC_CUDA( cudaStreamSynchronize( s ) );
+    return PCCB200_OK;
   } );
 }
 

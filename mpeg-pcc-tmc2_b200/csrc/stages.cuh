@@ -85,6 +85,8 @@ struct AttrImages {
 int    packPatches( CanvasPatch* dPatches, int numPatches, const uint8_t* occArena, int sizeU, int sizeV, int occRes, int* dResult, cudaStream_t s );
 void   formOccupancyAndGeometry( const CanvasPatch* dPatches, int numPatches, int maxPatchPixels, int maxPatchBlocks, const int16_t* depthArena,
                                  int occRes, int prec, int W, int H, CanvasImages& im, cudaStream_t s );
+void   blockToPatchFromVideo( const CanvasPatch* dPatches, int numPatches, int maxPatchBlocks, int occRes, int prec, int W, int H, const uint8_t* om,
+                              uint32_t* blockToPatch, cudaStream_t s );
 size_t reconstructPoints( const CanvasPatch* dPatches, const long long* dElemBase, int numPatches, long long totalElems, int occRes, int prec, int W,
                           int H, const uint8_t* om, const uint32_t* blockToPatch, const uint16_t* geo0, const uint16_t* geo1, ReconScratch& rc,
                           cudaStream_t s );

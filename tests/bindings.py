@@ -627,3 +627,35 @@ class ProductGof:
         if self.h:
             self.p.lib.pccb200_gof_free(self.h)
             self.h = C.c_void_p()
+
+
+def _product_generate_point_cloud(self, patches, occ_video, geo0, geo1, width, height, occupancy_precision=4):
+    """decoder-side PCCCodec::generatePointCloud: returns dict(xyz, point_to_pixel, partition, boundary)"""
+    L = self.lib
+    L.pccb200_generate_point_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_u8p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16), C.c_size_t,
+                                               C.c_size_t, C.c_int, C.c_size_t, c_i16p, c_u32p, c_u32p, C.POINTER(C.c_uint16), C.POINTER(C.c_size_t)]
+    patches = np.ascontiguousarray(patches)
+    occ_video, geo0, geo1 = (np.ascontiguousarray(a) for a in (occ_video, geo0, geo1))
+    u16p = C.POINTER(C.c_uint16)
+    r = C.c_size_t(0)
+    args = (self.ctx, patches.ctypes.data_as(C.c_void_p), len(patches), ptr(occ_video, c_u8p), ptr(geo0, u16p), ptr(geo1, u16p), width, height,
+            occupancy_precision)
+    self._check(L.pccb200_generate_point_cloud(*args, 0, None, None, None, None, C.byref(r)))
+    R = r.value
+    xyz, p2p = np.zeros((R, 3), np.int16), np.zeros((R, 3), np.uint32)
+    part, bnd = np.zeros(R, np.uint32), np.zeros(R, np.uint16)
+    self._check(L.pccb200_generate_point_cloud(*args, R, ptr(xyz, c_i16p), ptr(p2p, c_u32p), ptr(part, c_u32p), ptr(bnd, u16p), C.byref(r)))
+    return dict(xyz=xyz, point_to_pixel=p2p, partition=part, boundary=bnd)
+
+
+def _gof_set_decoded(self, f, occ_video=None, geo0=None, geo1=None):
+    L = self.p.lib
+    u16p = C.POINTER(C.c_uint16)
+    L.pccb200_gof_set_decoded.argtypes = [C.c_void_p, C.c_int, c_u8p, u16p, u16p]
+    keep = [None if a is None else np.ascontiguousarray(a) for a in (occ_video, geo0, geo1)]
+    self.p._check(L.pccb200_gof_set_decoded(self.h, f, None if keep[0] is None else ptr(keep[0], c_u8p),
+                                            None if keep[1] is None else ptr(keep[1], u16p), None if keep[2] is None else ptr(keep[2], u16p)))
+
+
+Product.generate_point_cloud = _product_generate_point_cloud
+ProductGof.set_decoded = _gof_set_decoded

@@ -39,3 +39,39 @@ def test_encode_gof_vs_reference_if_built(product):
     prm = ctc_seg_params(bits=10, iterations=10, weight=product.weight_normal(frames[0][0], 11))
     want, _ = ref.encode_gof(frames, prm)
     assert compare_gof(product.encode_gof(frames, prm), want) == []
+
+
+def test_decoder_side_generate_point_cloud(oracle, product):
+    """PCCCodec::generatePointCloud as PCCDecoder calls it: patch records + decoded planes in, cloud out."""
+    frames = [synth.figure(scale=0.2, seed=7, frame=0), synth.double_sheet(n_side=48, seed=1)]
+    prm = ctc_seg_params(bits=10, iterations=8, weight=product.weight_normal(frames[0][0], 11))
+    want = oracle.encode_gof(frames, prm, stop_after=3)
+    for fr in want:
+        got = product.generate_point_cloud(fr.patches.patches, fr[bindings.GOF_OM_VIDEO], fr[bindings.GOF_GEO0], fr[bindings.GOF_GEO1], fr.width, fr.height)
+        assert np.array_equal(got["xyz"].ravel(), fr[bindings.GOF_REC_XYZ])
+        assert np.array_equal(got["point_to_pixel"].ravel(), fr[bindings.GOF_POINT_TO_PIXEL])
+        assert np.array_equal(got["partition"], fr[bindings.GOF_REC_PARTITION])
+        assert np.array_equal(got["boundary"], fr[bindings.GOF_REC_BOUNDARY])
+
+
+def test_lossy_codec_round_trip_protocol(oracle, product):
+    """stop after the geometry images, hand 'decoded' planes back, resume: identity planes reproduce the one-shot result and
+    perturbed planes reproduce what the decoder-side entry point reconstructs from the same planes."""
+    frames = [synth.figure(scale=0.2, seed=3, frame=1)]
+    prm = ctc_seg_params(bits=10, iterations=8, weight=product.weight_normal(frames[0][0], 11))
+    one_shot = product.encode_gof(frames, prm)
+    g = bindings.ProductGof(product, frames, prm, 4)
+    W, H, _ = g.dims(0)
+    g.resume(W, H, 2)
+    om, g0, g1 = g.fetch(0, bindings.GOF_OM_VIDEO), g.fetch(0, bindings.GOF_GEO0), g.fetch(0, bindings.GOF_GEO1)
+    assert np.array_equal(g0, one_shot[0][bindings.GOF_GEO0]) and np.array_equal(om, one_shot[0][bindings.GOF_OM_VIDEO])
+    noisy0 = np.clip(g0.astype(np.int32) + (np.arange(g0.size) % 3 == 0), 0, 255).astype(np.uint16)   # a 'lossy' D0
+    noisy1 = np.maximum(noisy0, g1)
+    g.set_decoded(0, om, noisy0, noisy1)
+    g.resume(W, H, 0)
+    rec = g.fetch(0, bindings.GOF_REC_XYZ)
+    p2p = g.fetch(0, bindings.GOF_POINT_TO_PIXEL)
+    g.free()
+    ref = product.generate_point_cloud(one_shot[0].patches.patches, om, noisy0, noisy1, W, H)
+    assert np.array_equal(rec, ref["xyz"].ravel()) and np.array_equal(p2p, ref["point_to_pixel"].ravel())
+    assert not np.array_equal(rec, one_shot[0][bindings.GOF_REC_XYZ])
