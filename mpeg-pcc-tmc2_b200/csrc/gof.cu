@@ -94,7 +94,7 @@ void segmentFrame( FrameState& fs, const pccb200_seg_params& prm ) {
   if ( prm.normal_orientation == 1 ) {
     ProfScope t( pf, "orient", s );
     fs.orient.prof = pf;
-    orientNormals( fs.orient, fs.xyz4, fs.nbr, k, n, fs.normals, s );
+    orientNormals( fs.orient, fs.xyz4, fs.nbr, k, fs.tree.vind, n, fs.normals, s );
   }
   {
     ProfScope t( pf, "initial_seg", s );

@@ -71,189 +71,246 @@ __global__ void __launch_bounds__( 128 )
   }
 }
 
-// after the sort: rank of every edge and the (start, end|rel) record of every rank
-__global__ void kRanks( const uint32_t* __restrict__ sortedIds, const uint32_t* __restrict__ nbrSorted,
-                        const uint32_t* __restrict__ relBits, size_t E, uint32_t* __restrict__ rankRel, uint2* __restrict__ byRank ) {
+// after the sort: rank (+ relative-sign bits) of every edge slot
+__global__ void kRanks( const uint32_t* __restrict__ sortedIds, const uint32_t* __restrict__ relBits, size_t E, uint32_t* __restrict__ rankRel ) {
   const size_t r = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
   if ( r >= E ) return;
   const uint32_t e = sortedIds[r];
   rankRel[e]       = uint32_t( r ) | relBits[e];
-  byRank[r]        = make_uint2( e >> 4, nbrSorted[e] | relBits[e] );  // end < 2^30 (E < 2^30)
+}
+
+__global__ void kInvert( const uint32_t* __restrict__ vind, int n, uint32_t* __restrict__ pos ) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( p < n ) pos[vind[p]] = p;
+}
+
+// The walk works on TREE POSITIONS (kd-tree leaf order): neighbours in space are neighbours in memory, so the frontier the
+// walk is working on stays in L2. One 128-byte row per point: 16 x (neighbour position, rank | relative sign), slots in
+// ascending ORIGINAL neighbour index (the tie-break order of the keys).
+__global__ void kBuildRows( const uint32_t* __restrict__ vind, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ nbrSorted,
+                            const uint32_t* __restrict__ rankRel, int n, uint2* __restrict__ rows ) {
+  const size_t t = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( t >= size_t( n ) * 16 ) return;
+  const uint32_t p = uint32_t( t >> 4 ), slot = uint32_t( t & 15 );
+  const size_t   e = size_t( vind[p] ) * 16 + slot;
+  const uint32_t j = nbrSorted[e];
+  rows[t]          = make_uint2( j == kInvalid ? kInvalid : pos[j], rankRel[e] );
 }
 
 struct WalkArgs {
-  const uint32_t* nbr;        // n x k, original k-NN order (seed sign only)
-  const uint32_t* nbrSorted;  // n x 16
-  const uint32_t* rankRel;    // n x 16
-  const uint2*    byRank;     // E
-  const double*   normals;    // original (unoriented) normals
-  const short4*   pts;
-  uint64_t*       L0;    // E/64 words, zeroed
-  uint32_t*       best;  // n, kNone
-  uint8_t*        flip;  // n, 0
+  const uint32_t* nbr;      // n x k, original k-NN order and indices (seed sign only)
+  const uint32_t* pos;      // original index -> tree position
+  const uint2*    rows;     // n x 16 by tree position: (neighbour position, rank | rel)
+  uint32_t*       rankEnd;  // E: end position | (flip-the-end bit << 31) of the edge holding a rank; written when the rank is queued
+  const double*   normals;  // original (unoriented) normals, original order
+  const short4*   pts;      // original order
+  uint64_t*       L0;       // E/64 words, zeroed: leaf level of the priority queue (one bit per rank)
+  uint32_t*       best;     // by position: kNone / rank of the queued incoming edge / kVisited
+  uint8_t*        flip;     // by position
   int             n, k;
-  int             nL0, nL1, nL2, nL3;
+  int             nL1, nL2, nL3, nL4;  // 32-ary upper levels in shared memory
 };
 
-__device__ __forceinline__ int topBit( uint64_t w ) { return 63 - __clzll( (long long)w ); }
+__device__ __forceinline__ int  topBit64( uint64_t w ) { return 63 - __clzll( (long long)w ); }
+__device__ __forceinline__ int  topBit32( uint32_t w ) { return 31 - __clz( int( w ) ); }
+__device__ __forceinline__ void prefetchL2( const void* p ) { asm volatile( "prefetch.global.L2 [%0];" ::"l"( p ) ); }
 
-// 1 warp. Lane 0 drives; lanes 0..15 expand the neighbours of the newly visited point.
+// Upper levels of the bit-tree: level l has one bit per word of level l-1. L1 indexes the 64-bit leaf words.
+struct Levels {
+  uint32_t *L1, *L2, *L3, *L4;
+  __device__ __forceinline__ void set( uint32_t rank ) const {
+    uint32_t w = rank >> 6;  // leaf word
+    atomicOr( &L1[w >> 5], 1u << ( w & 31 ) );
+    w >>= 5;
+    atomicOr( &L2[w >> 5], 1u << ( w & 31 ) );
+    w >>= 5;
+    atomicOr( &L3[w >> 5], 1u << ( w & 31 ) );
+    w >>= 5;
+    atomicOr( &L4[w >> 5], 1u << ( w & 31 ) );
+  }
+  // leaf word `w` has just become empty: clear its bit and cascade while words drain
+  __device__ __forceinline__ void leafEmptied( uint32_t w ) const {
+    uint32_t bit = 1u << ( w & 31 );
+    uint32_t o   = atomicAnd( &L1[w >> 5], ~bit );
+    if ( o & ~bit ) return;
+    w >>= 5, bit = 1u << ( w & 31 );
+    o = atomicAnd( &L2[w >> 5], ~bit );
+    if ( o & ~bit ) return;
+    w >>= 5, bit = 1u << ( w & 31 );
+    o = atomicAnd( &L3[w >> 5], ~bit );
+    if ( o & ~bit ) return;
+    w >>= 5;
+    atomicAnd( &L4[w >> 5], ~( 1u << ( w & 31 ) ) );
+  }
+  // index of the highest non-empty leaf word, or -1
+  __device__ __forceinline__ int topLeaf( int nL4 ) const {
+    int w4 = nL4 - 1;
+    while ( w4 >= 0 && L4[w4] == 0 ) --w4;
+    if ( w4 < 0 ) return -1;
+    const uint32_t i3 = uint32_t( w4 ) * 32 + topBit32( L4[w4] );
+    const uint32_t i2 = i3 * 32 + topBit32( L3[i3] );
+    const uint32_t i1 = i2 * 32 + topBit32( L2[i2] );
+    return int( i1 * 32 + topBit32( L1[i1] ) );
+  }
+};
+
+// One warp. Lanes 0..15 expand the 16 neighbour slots of the point being visited; lane 16 ("scout") concurrently finds the
+// largest rank already queued. The next point is the larger of the scout's find and the best rank queued in this very step,
+// which is still in registers — so the dependent chain per visited point is rows -> best[] -> clear-return (lanes) in
+// parallel with leaf word -> rankEnd (scout): about three L2 round trips.
 __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
-  extern __shared__ uint64_t smem[];
-  uint64_t*                  L1   = smem;
-  uint64_t*                  L2   = L1 + a.nL1;
-  uint64_t*                  L3   = L2 + a.nL2;
+  extern __shared__ uint32_t smem32[];
+  Levels                     lv{ smem32, smem32 + a.nL1, smem32 + a.nL1 + a.nL2, smem32 + a.nL1 + a.nL2 + a.nL3 };
   const int                  lane = threadIdx.x;
-  for ( int i = lane; i < a.nL1 + a.nL2 + a.nL3; i += 32 ) smem[i] = 0;
+  for ( int i = lane; i < a.nL1 + a.nL2 + a.nL3 + a.nL4; i += 32 ) smem32[i] = 0;
   __syncwarp();
 
-  auto finalNormal = [&]( uint32_t i, double out[3] ) {
-    const double s = a.flip[i] ? -1.0 : 1.0;
-    out[0] = s * a.normals[3 * size_t( i )], out[1] = s * a.normals[3 * size_t( i ) + 1], out[2] = s * a.normals[3 * size_t( i ) + 2];
+  auto finalNormal = [&]( uint32_t orig, double out[3] ) {
+    const double s = a.flip[a.pos[orig]] ? -1.0 : 1.0;
+    out[0] = s * a.normals[3 * size_t( orig )], out[1] = s * a.normals[3 * size_t( orig ) + 1], out[2] = s * a.normals[3 * size_t( orig ) + 2];
   };
 
-  // push / improve the frontier entries of `cur`'s unvisited neighbours (lanes 0..15)
-  auto expand = [&]( uint32_t cur ) {
-    uint32_t setRank = kNone, clrRank = kNone;
-    if ( lane < 16 ) {
-      const size_t   e = size_t( cur ) * 16 + lane;
-      const uint32_t j = a.nbrSorted[e];
-      if ( j != kInvalid ) {
-        const uint32_t old = __ldcg( &a.best[j] );
-        if ( old != kVisited ) {
-          const uint32_t r = a.rankRel[e] & kRankMask;
-          if ( old == kNone || r > old ) {
-            a.best[j] = r;
-            setRank   = r;
-            clrRank   = old;
-          }
-        }
-      }
-    }
-    __syncwarp();
-    if ( clrRank != kNone ) {  // remove the superseded entry, emptying upper levels when a word drains
-      uint64_t bit = 1ull << ( clrRank & 63 );
-      uint64_t o   = atomicAnd( (unsigned long long*)&a.L0[clrRank >> 6], ~bit );
-      if ( ( o & ~bit ) == 0 ) {
-        uint32_t w = clrRank >> 6;
-        bit        = 1ull << ( w & 63 );
-        o          = atomicAnd( (unsigned long long*)&L1[w >> 6], ~bit );
-        if ( ( o & ~bit ) == 0 ) {
-          w >>= 6;
-          bit = 1ull << ( w & 63 );
-          o   = atomicAnd( (unsigned long long*)&L2[w >> 6], ~bit );
-          if ( ( o & ~bit ) == 0 ) {
-            w >>= 6;
-            atomicAnd( (unsigned long long*)&L3[w >> 6], ~( 1ull << ( w & 63 ) ) );
-          }
-        }
-      }
-    }
-    __syncwarp();
-    if ( setRank != kNone ) {
-      uint32_t w = setRank;
-      atomicOr( (unsigned long long*)&a.L0[w >> 6], 1ull << ( w & 63 ) );
-      w >>= 6;
-      atomicOr( (unsigned long long*)&L1[w >> 6], 1ull << ( w & 63 ) );
-      w >>= 6;
-      atomicOr( (unsigned long long*)&L2[w >> 6], 1ull << ( w & 63 ) );
-      w >>= 6;
-      atomicOr( (unsigned long long*)&L3[w >> 6], 1ull << ( w & 63 ) );
-    }
-    __threadfence_block();
-    __syncwarp();
-  };
+  // scout state (lane 16): a leaf word whose bit was removed at the end of the previous step; its old value decides whether
+  // the upper levels must be fixed (done before the next descent, never across a set phase)
+  bool     removalPending = false;
+  uint64_t removalOld = 0, removalBit = 0;
+  uint32_t removalWord = 0;
 
-  // seeds in ascending index: scan 32 candidates per coalesced load, re-check each before use (a tree grown from
-  // an earlier seed of the chunk may have swallowed a later one)
-  for ( uint32_t base = 0; base < uint32_t( a.n ); base += 32 ) {
-   unsigned pending = __ballot_sync( 0xffffffffu, base + lane < uint32_t( a.n ) && __ldcg( &a.best[base + lane] ) != kVisited );
-   while ( pending ) {
-    const uint32_t seed = base + ( __ffs( pending ) - 1 );
-    pending &= pending - 1;
-    if ( __ldcg( &a.best[seed] ) == kVisited ) continue;  // warp-uniform
-    // ---- new tree: orient the seed from its already-visited neighbours (reference order of the k-NN list)
-    if ( lane == 0 ) {
-      double acc[3] = {0.0, 0.0, 0.0};
-      int    cnt    = 0;
-      for ( int t = 0; t < a.k; ++t ) {
-        const uint32_t j = a.nbr[size_t( seed ) * a.k + t];
-        if ( j == kInvalid ) break;
-        if ( j != seed && __ldcg( &a.best[j] ) == kVisited ) {
-          double nj[3];
-          finalNormal( j, nj );
-          acc[0] = acc[0] + nj[0], acc[1] = acc[1] + nj[1], acc[2] = acc[2] + nj[2];
-          ++cnt;
-        }
-      }
-      if ( cnt == 0 ) {
-        if ( seed != 0 ) {
-          finalNormal( seed - 1, acc );
-        } else {
-          const short4 p = a.pts[0];
-          acc[0] = 0.0 - double( p.x ), acc[1] = 0.0 - double( p.y ), acc[2] = 0.0 - double( p.z );
-        }
-      }
-      const double* ns = a.normals + 3 * size_t( seed );
-      if ( ns[0] * acc[0] + ns[1] * acc[1] + ns[2] * acc[2] < 0.0 ) a.flip[seed] = 1;
-      // remove the seed's own frontier entry, if any, then mark it visited
-      const uint32_t old = a.best[seed];
-      a.best[seed]       = kVisited;
-      (void)old;  // the queue is empty between trees, so the seed has no frontier entry to remove
-    }
-    __threadfence_block();
-    __syncwarp();
-    expand( seed );
-    // ---- grow: pop the largest rank until the queue is empty
+  // grows one tree from position `cur` (already marked visited, flip decided) until the queue is empty
+  auto grow = [&]( uint32_t cur, bool curFlip ) {
     for ( ;; ) {
-      uint32_t r = kNone;
-      if ( lane == 0 ) {
-        int w3 = a.nL3 - 1;
-        while ( w3 >= 0 && L3[w3] == 0 ) --w3;
-        if ( w3 >= 0 ) {
-          const uint32_t i2 = uint32_t( w3 ) * 64 + topBit( L3[w3] );
-          const uint32_t i1 = i2 * 64 + topBit( L2[i2] );
-          const uint32_t i0 = i1 * 64 + topBit( L1[i1] );
-          const uint64_t w0 = __ldcg( (const unsigned long long*)&a.L0[i0] );
-          const int      b  = topBit( w0 );
-          r                 = i0 * 64 + b;
-          const uint64_t nw = w0 & ~( 1ull << b );
-          atomicAnd( (unsigned long long*)&a.L0[i0], ~( 1ull << b ) );
-          if ( nw == 0 ) {
-            L1[i1] &= ~( 1ull << ( i0 & 63 ) );
-            if ( L1[i1] == 0 ) {
-              L2[i2] &= ~( 1ull << ( i1 & 63 ) );
-              if ( L2[i2] == 0 ) L3[w3] &= ~( 1ull << ( i2 & 63 ) );
-            }
-          }
+      // ---- phase 1: issue the independent loads
+      uint2 slot = make_uint2( kInvalid, 0 );
+      if ( lane < 16 ) slot = a.rows[size_t( cur ) * 16 + lane];
+      int      leaf = -1;
+      uint64_t w0   = 0;
+      if ( lane == 16 ) {
+        if ( removalPending ) {
+          if ( ( removalOld & ~removalBit ) == 0 ) lv.leafEmptied( removalWord );
+          removalPending = false;
+        }
+        leaf = lv.topLeaf( a.nL4 );
+        if ( leaf >= 0 ) w0 = __ldcg( (const unsigned long long*)&a.L0[leaf] );
+      }
+      // ---- phase 2: dependent loads
+      uint32_t old = kVisited;
+      if ( lane < 16 && slot.x != kInvalid ) old = __ldcg( &a.best[slot.x] );
+      uint32_t rB = 0, infoB = 0;  // rank + 1 of the scout's find (0 = none)
+      if ( lane == 16 && leaf >= 0 ) {
+        // (w0 cannot be 0: the upper levels are exact at this point)
+        const int b = topBit64( w0 );
+        rB          = uint32_t( leaf ) * 64 + b + 1;
+        infoB       = __ldcg( &a.rankEnd[rB - 1] );
+      }
+      // ---- phase 3: queue / improve the frontier entries of the unvisited neighbours
+      const uint32_t r        = slot.y & kRankMask;
+      const bool     improved = old != kVisited && ( old == kNone || r > old );
+      const bool     flipEnd  = curFlip ? ( slot.y & kRelPos ) != 0 : ( slot.y & kRelNeg ) != 0;  // n_cur(final) . n_j(original) < 0
+      if ( improved ) {
+        a.best[slot.x] = r;
+        a.rankEnd[r]   = slot.x | ( flipEnd ? 0x80000000u : 0u );  // also brings the line into L2 for the later pop
+        prefetchL2( a.rows + size_t( slot.x ) * 16 );                // the row the visit of slot.x will read
+      }
+      const uint32_t myCand = improved ? r + 1 : 0;
+      const uint32_t A      = __reduce_max_sync( 0xffffffffu, myCand );
+      rB                    = __shfl_sync( 0xffffffffu, rB, 16 );
+      if ( A == 0 && rB == 0 ) return;  // queue empty, nothing queued: this tree is complete
+      const bool newWins = A > rB;      // (a superseded scout find always loses: its replacement has a larger rank)
+      // superseded entries leave the queue; a drained leaf word is unhooked from the upper levels right away
+      if ( improved && old != kNone ) {
+        const uint64_t bit = 1ull << ( old & 63 );
+        const uint64_t o   = atomicAnd( (unsigned long long*)&a.L0[old >> 6], ~bit );
+        if ( ( o & ~bit ) == 0 ) lv.leafEmptied( old >> 6 );
+      }
+      __syncwarp();
+      // new entries enter the queue — except the one that is visited next
+      if ( improved && !( newWins && myCand == A ) ) {
+        atomicOr( (unsigned long long*)&a.L0[r >> 6], 1ull << ( r & 63 ) );
+        lv.set( r );
+      }
+      uint32_t next;
+      bool     nextFlip;
+      if ( newWins ) {
+        const int src = __ffs( __ballot_sync( 0xffffffffu, myCand == A ) ) - 1;
+        next          = __shfl_sync( 0xffffffffu, slot.x, src );
+        nextFlip      = __shfl_sync( 0xffffffffu, int( flipEnd ), src ) != 0;
+      } else {
+        infoB    = __shfl_sync( 0xffffffffu, infoB, 16 );
+        next     = infoB & 0x7fffffffu;
+        nextFlip = ( infoB >> 31 ) != 0;
+        if ( lane == 16 ) {  // take the scout's find out of the queue; the upper levels are fixed at the start of the next step
+          const uint32_t rank = rB - 1;
+          removalBit          = 1ull << ( rank & 63 );
+          removalWord         = rank >> 6;
+          removalOld          = atomicAnd( (unsigned long long*)&a.L0[removalWord], ~removalBit );
+          removalPending      = true;
         }
       }
-      r = __shfl_sync( 0xffffffffu, r, 0 );
-      if ( r == kNone ) break;
-      const uint2    se    = a.byRank[r];
-      const uint32_t start = se.x, end = se.y & kRankMask, relHere = se.y & ( kRelNeg | kRelPos );
       if ( lane == 0 ) {
-        const bool startFlipped = a.flip[start] != 0;
-        // normals_[start] (final) . normals_[end] (original) < 0 ?
-        const bool flipEnd = startFlipped ? ( relHere & kRelPos ) != 0 : ( relHere & kRelNeg ) != 0;
-        a.flip[end]        = flipEnd ? 1 : 0;
-        a.best[end]        = kVisited;
+        a.flip[next] = nextFlip ? 1 : 0;
+        a.best[next] = kVisited;
       }
       __threadfence_block();
       __syncwarp();
-      expand( end );
+      cur = next, curFlip = nextFlip;
     }
-   }
+  };
+
+  // seeds in ascending ORIGINAL index: scan 32 candidates per load, re-check each before use (a tree grown from an earlier
+  // seed of the chunk may have swallowed a later one)
+  for ( uint32_t base = 0; base < uint32_t( a.n ); base += 32 ) {
+    const bool     inRange = base + lane < uint32_t( a.n );
+    const uint32_t myPos   = inRange ? a.pos[base + lane] : 0;
+    unsigned       pending = __ballot_sync( 0xffffffffu, inRange && __ldcg( &a.best[myPos] ) != kVisited );
+    while ( pending ) {
+      const int      sl   = __ffs( pending ) - 1;
+      const uint32_t seed = base + sl;  // original index
+      pending &= pending - 1;
+      const uint32_t seedPos = __shfl_sync( 0xffffffffu, myPos, sl );
+      if ( __ldcg( &a.best[seedPos] ) == kVisited ) continue;  // warp-uniform
+      // ---- new tree: orient the seed from its already-visited neighbours (reference order of the k-NN list)
+      int seedFlip = 0;
+      if ( lane == 0 ) {
+        double acc[3] = {0.0, 0.0, 0.0};
+        int    cnt    = 0;
+        for ( int t = 0; t < a.k; ++t ) {
+          const uint32_t j = a.nbr[size_t( seed ) * a.k + t];
+          if ( j == kInvalid ) break;
+          if ( j != seed && __ldcg( &a.best[a.pos[j]] ) == kVisited ) {
+            double nj[3];
+            finalNormal( j, nj );
+            acc[0] = acc[0] + nj[0], acc[1] = acc[1] + nj[1], acc[2] = acc[2] + nj[2];
+            ++cnt;
+          }
+        }
+        if ( cnt == 0 ) {
+          if ( seed != 0 ) {
+            finalNormal( seed - 1, acc );
+          } else {
+            const short4 p = a.pts[0];
+            acc[0] = 0.0 - double( p.x ), acc[1] = 0.0 - double( p.y ), acc[2] = 0.0 - double( p.z );
+          }
+        }
+        const double* ns = a.normals + 3 * size_t( seed );
+        seedFlip         = ns[0] * acc[0] + ns[1] * acc[1] + ns[2] * acc[2] < 0.0 ? 1 : 0;
+        a.flip[seedPos]  = uint8_t( seedFlip );
+        a.best[seedPos]  = kVisited;  // the queue is empty between trees: the seed has no entry to remove
+      }
+      seedFlip = __shfl_sync( 0xffffffffu, seedFlip, 0 );
+      __threadfence_block();
+      __syncwarp();
+      grow( seedPos, seedFlip != 0 );
+    }
   }
 }
 
-__global__ void kApplyFlip( double* __restrict__ normals, const uint8_t* __restrict__ flip, const short4* __restrict__ pts, int n,
+__global__ void kApplyFlip( double* __restrict__ normals, const uint8_t* __restrict__ flip, const uint32_t* __restrict__ pos, const short4* __restrict__ pts, int n,
                             unsigned int* __restrict__ negCount ) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool      neg = false;
   if ( i < n ) {
     double x = normals[3 * size_t( i )], y = normals[3 * size_t( i ) + 1], z = normals[3 * size_t( i ) + 2];
-    if ( flip[i] ) {
+    if ( flip[pos[i]] ) {
       x = -x, y = -y, z = -z;
       normals[3 * size_t( i )] = x, normals[3 * size_t( i ) + 1] = y, normals[3 * size_t( i ) + 2] = z;
     }
@@ -277,33 +334,37 @@ __global__ void kFillU32( uint32_t* p, size_t n, uint32_t v ) {
 
 }  // namespace
 
-void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, size_t n, double* normals, cudaStream_t s ) {
+void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
+                    cudaStream_t s ) {
   if ( n == 0 ) return;
   if ( k > 16 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   const size_t E = n * 16;
   if ( E > size_t( kRankMask ) ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   sc.nbrSorted.reserve( E ), sc.relBits.reserve( E ), sc.keysA.reserve( E ), sc.keysB.reserve( E );
-  sc.idsA.reserve( E ), sc.idsB.reserve( E ), sc.rankRel.reserve( E ), sc.byRank.reserve( E );
+  sc.idsA.reserve( E ), sc.idsB.reserve( E ), sc.rankRel.reserve( E ), sc.rankEnd.reserve( E ), sc.rows.reserve( E ), sc.pos.reserve( n );
   kEdgeKeys<<<divUp( n, 128 ), 128, 0, s>>>( nbr, normals, int( n ), k, sc.nbrSorted, sc.relBits, sc.keysA, sc.idsA );
   PCC_LAUNCH_CHECK();
   size_t tmpBytes = 0;
   PCC_CUDA( cub::DeviceRadixSort::SortPairs( nullptr, tmpBytes, sc.keysA.p, sc.keysB.p, sc.idsA.p, sc.idsB.p, E, 0, 62, s ) );
   sc.cubTmp.reserve( tmpBytes + 16 );
   PCC_CUDA( cub::DeviceRadixSort::SortPairs( sc.cubTmp.p, tmpBytes, sc.keysA.p, sc.keysB.p, sc.idsA.p, sc.idsB.p, E, 0, 62, s ) );
-  kRanks<<<divUp( E, 256 ), 256, 0, s>>>( sc.idsB, sc.nbrSorted, sc.relBits, E, sc.rankRel, sc.byRank );
+  kRanks<<<divUp( E, 256 ), 256, 0, s>>>( sc.idsB, sc.relBits, E, sc.rankRel );
+  kInvert<<<divUp( n, 256 ), 256, 0, s>>>( vind, int( n ), sc.pos );
+  kBuildRows<<<divUp( E, 256 ), 256, 0, s>>>( vind, sc.pos, sc.nbrSorted, sc.rankRel, int( n ), sc.rows );
   PCC_LAUNCH_CHECK();
 
   WalkArgs a;
-  a.nbr = nbr, a.nbrSorted = sc.nbrSorted, a.rankRel = sc.rankRel, a.byRank = sc.byRank, a.normals = normals, a.pts = pts;
+  a.nbr = nbr, a.pos = sc.pos, a.rows = sc.rows, a.rankEnd = sc.rankEnd, a.normals = normals, a.pts = pts;
   a.n = int( n ), a.k = k;
-  a.nL0 = int( ( E + 63 ) / 64 ), a.nL1 = ( a.nL0 + 63 ) / 64, a.nL2 = ( a.nL1 + 63 ) / 64, a.nL3 = ( a.nL2 + 63 ) / 64;
-  sc.L0.reserve( a.nL0 + 1 ), sc.best.reserve( n ), sc.flip.reserve( n ), sc.counter.reserve( 4 );
-  PCC_CUDA( cudaMemsetAsync( sc.L0, 0, size_t( a.nL0 ) * 8, s ) );
+  const int nL0 = int( ( E + 63 ) / 64 );
+  a.nL1 = ( nL0 + 31 ) / 32, a.nL2 = ( a.nL1 + 31 ) / 32, a.nL3 = ( a.nL2 + 31 ) / 32, a.nL4 = ( a.nL3 + 31 ) / 32;
+  sc.L0.reserve( nL0 + 1 ), sc.best.reserve( n ), sc.flip.reserve( n ), sc.counter.reserve( 4 );
+  PCC_CUDA( cudaMemsetAsync( sc.L0, 0, size_t( nL0 ) * 8, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.flip, 0, n, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.counter, 0, sizeof( unsigned ), s ) );
   kFillU32<<<divUp( n, 256 ), 256, 0, s>>>( sc.best, n, kNone );
   a.L0 = sc.L0, a.best = sc.best, a.flip = sc.flip;
-  const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 ) * 8;
+  const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 + a.nL4 ) * 4;
   if ( smemBytes > 200 * 1024 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   {  // the limit is a per-function global: raise it once to the maximum any frame may need (frames run on concurrent host threads)
     static std::once_flag once;
@@ -316,11 +377,11 @@ void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, i
     kWalk<<<1, 32, smemBytes, s>>>( a );
     PCC_LAUNCH_CHECK();
   }
-  // The walk runs for seconds on one warp. Nothing that depends on it is enqueued until it has finished: a dependent
+  // The walk runs for a long time on one warp. Nothing that depends on it is enqueued until it has finished: a dependent
   // launch waiting at the head of a hardware queue would stall unrelated kernels of other frames' streams that share the
   // queue (CUDA_DEVICE_MAX_CONNECTIONS queues for all streams). The per-frame host thread simply waits here.
   PCC_CUDA( cudaStreamSynchronize( s ) );
-  kApplyFlip<<<divUp( n, 256 ), 256, 0, s>>>( normals, sc.flip, pts, int( n ), sc.counter );
+  kApplyFlip<<<divUp( n, 256 ), 256, 0, s>>>( normals, sc.flip, sc.pos, pts, int( n ), sc.counter );
   kNegateIfMajority<<<divUp( 3 * n, 256 ), 256, 0, s>>>( normals, int( n ), sc.counter );
   PCC_LAUNCH_CHECK();
 }

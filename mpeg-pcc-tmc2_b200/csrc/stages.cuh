@@ -11,14 +11,15 @@ void initialSegmentation( const double* normals, size_t n, const double w[3], ui
 
 // orient.cu
 struct OrientScratch {
-  DevBuf<uint32_t> nbrSorted, relBits, idsA, idsB, rankRel, best;
+  DevBuf<uint32_t> nbrSorted, relBits, idsA, idsB, rankRel, best, pos, rankEnd;
+  DevBuf<uint2>    rows;
   DevBuf<uint64_t> keysA, keysB, L0;
-  DevBuf<uint2>    byRank;
   DevBuf<uint8_t>  flip, cubTmp;
   DevBuf<unsigned> counter;
   Profiler*        prof = nullptr;
 };
-void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, size_t n, double* normals, cudaStream_t s );
+void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
+                    cudaStream_t s );
 
 // refine.cu
 struct RefineScratch {
