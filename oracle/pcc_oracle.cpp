@@ -1023,8 +1023,17 @@ void pushPull( Img3& image, const std::vector<uint8_t>& occ ) {
 
 }  // namespace
 
+void* pcco_encode_gof_canvas( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                              const pccb200_seg_params* prm, int occPrec, int stopAfter, size_t forceW, size_t forceH );
+
 void* pcco_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
                        const pccb200_seg_params* prm, int occPrec, int stopAfter ) {
+  return pcco_encode_gof_canvas( nframes, xyz, rgb, n, prm, occPrec, stopAfter, 0, 0 );
+}
+
+// forceW/forceH (0 = none): lower bound for the canvas, i.e. the all-reduced size when the GOF's frames are sharded over ranks
+void* pcco_encode_gof_canvas( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                              const pccb200_seg_params* prm, int occPrec, int stopAfter, size_t forceW, size_t forceH ) {
   OGof* G = new OGof();
   G->frames.resize( nframes );
   const int occRes = prm->occupancy_resolution;
@@ -1041,6 +1050,7 @@ void* pcco_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* co
   size_t W = minW, H = minH;
   for ( auto& F : G->frames ) W = std::max( W, F.width ), H = std::max( H, F.height );
   W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
+  W = std::max( W, forceW ), H = std::max( H, forceH );
   for ( auto& F : G->frames ) F.width = W, F.height = H;
   if ( stopAfter == 1 ) return G;
   const size_t bw = W / occRes, bh = H / occRes, ow = W / occPrec, oh = H / occPrec;

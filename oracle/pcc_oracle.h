@@ -65,6 +65,9 @@ void* pcco_segment_frame( const int16_t* xyz, const uint8_t* rgb, size_t n, cons
  * stop_after: 0 all, 1 packing, 2 geometry images, 3 generatePointCloud */
 void*  pcco_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
                         const pccb200_seg_params* p, int occupancy_precision, int stop_after );
+/* same with a lower bound on the canvas (frames of one GOF sharded over ranks: pass the all-reduced size) */
+void*  pcco_encode_gof_canvas( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
+                               const pccb200_seg_params* p, int occupancy_precision, int stop_after, size_t force_w, size_t force_h );
 void   pcco_gof_free( void* h );
 void   pcco_gof_dims( void* h, int f, size_t* w, size_t* hgt, size_t* rec_points );
 void*  pcco_gof_patches( void* h, int f ); /* borrowed patch list for pcco_patches_* */

@@ -477,10 +477,13 @@ def _ref_encode_gof(self, frames, params, occupancy_precision=4, stop_after=0):
 Reference.encode_gof = _ref_encode_gof
 
 
-def _generic_encode_gof(lib, prefix, frames, params, occupancy_precision=4, stop_after=0):
+def _generic_encode_gof(lib, prefix, frames, params, occupancy_precision=4, stop_after=0, canvas=None):
     g = lambda name: getattr(lib, prefix + name)
     g("encode_gof").restype = C.c_void_p
     g("encode_gof").argtypes = [C.c_int, C.POINTER(c_i16p), C.POINTER(c_u8p), C.POINTER(C.c_size_t), C.POINTER(SegParams), C.c_int, C.c_int]
+    if canvas is not None:
+        g("encode_gof_canvas").restype = C.c_void_p
+        g("encode_gof_canvas").argtypes = g("encode_gof").argtypes + [C.c_size_t, C.c_size_t]
     g("gof_free").argtypes = [C.c_void_p]
     g("gof_dims").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     g("gof_patches").restype = C.c_void_p
@@ -488,7 +491,10 @@ def _generic_encode_gof(lib, prefix, frames, params, occupancy_precision=4, stop
     g("gof_get").restype = C.c_size_t
     g("gof_get").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     n, xs, cs, xp, cp, ns = _frames_args(frames)
-    h = g("encode_gof")(n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after)
+    if canvas is not None:
+        h = g("encode_gof_canvas")(n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after, canvas[0], canvas[1])
+    else:
+        h = g("encode_gof")(n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after)
     out = []
     for f in range(n):
         fr = GofFrame()
@@ -507,8 +513,8 @@ def _generic_encode_gof(lib, prefix, frames, params, occupancy_precision=4, stop
     return out
 
 
-def _oracle_encode_gof(self, frames, params, occupancy_precision=4, stop_after=0):
-    return _generic_encode_gof(self.lib._dll, "pcco_", frames, params, occupancy_precision, stop_after)
+def _oracle_encode_gof(self, frames, params, occupancy_precision=4, stop_after=0, canvas=None):
+    return _generic_encode_gof(self.lib._dll, "pcco_", frames, params, occupancy_precision, stop_after, canvas)
 
 
 Oracle.encode_gof = _oracle_encode_gof
