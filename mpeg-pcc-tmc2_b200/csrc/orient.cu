@@ -154,14 +154,18 @@ struct Levels {
   }
 };
 
-// One warp. Lanes 0..15 expand the 16 neighbour slots of the point being visited; lane 16 ("scout") concurrently finds the
-// largest rank already queued. The next point is the larger of the scout's find and the best rank queued in this very step,
-// which is still in registers — so the dependent chain per visited point is rows -> best[] -> clear-return (lanes) in
-// parallel with leaf word -> rankEnd (scout): about three L2 round trips.
+// One warp per frame. Priority queue = a 32-entry HOT SET held in registers (one entry per lane: the most recently queued
+// edges, which the greedy walk pops next most of the time) + the global bit-tree (leaf words in global memory, 32-ary upper
+// levels in shared memory) for everything that spills. The largest queued rank is max(hot-set maximum, cached top of the
+// bit-tree); the cached top only has to be re-read (two dependent loads, done by lane 16 while lanes 0..15 expand) after it was
+// popped or superseded. Clears of the bit-tree are fire-and-forget: the touched leaf word is remembered and re-read before the
+// next descent, which keeps the upper levels exact without waiting for an atomic's return value.
+// Dependent chain per visited point in the common case: neighbour row -> best[] of the 16 neighbours.
 __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
   extern __shared__ uint32_t smem32[];
   Levels                     lv{ smem32, smem32 + a.nL1, smem32 + a.nL1 + a.nL2, smem32 + a.nL1 + a.nL2 + a.nL3 };
   const int                  lane = threadIdx.x;
+  const unsigned             FULL = 0xffffffffu;
   for ( int i = lane; i < a.nL1 + a.nL2 + a.nL3 + a.nL4; i += 32 ) smem32[i] = 0;
   __syncwarp();
 
@@ -170,85 +174,176 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
     out[0] = s * a.normals[3 * size_t( orig )], out[1] = s * a.normals[3 * size_t( orig ) + 1], out[2] = s * a.normals[3 * size_t( orig ) + 2];
   };
 
-  // scout state (lane 16): a leaf word whose bit was removed at the end of the previous step; its old value decides whether
-  // the upper levels must be fixed (done before the next descent, never across a set phase)
-  bool     removalPending = false;
-  uint64_t removalOld = 0, removalBit = 0;
-  uint32_t removalWord = 0;
+  uint32_t hotRank = 0, hotInfo = 0;      // per lane: rank + 1 (0 = free slot), end position | flip << 31
+  uint32_t pendingWord = kNone;           // per lane: a leaf word this lane cleared a bit in and has not re-checked yet
+  uint32_t gTop = 0, gTopInfo = 0;        // warp-uniform: cached maximum of the bit-tree (rank + 1, 0 = tree empty)
+  bool     gTopValid = true;              // warp-uniform
+#ifdef PCC_WALK_STATS
+  unsigned stNew = 0, stHot = 0, stTree = 0, stRefresh = 0, stStale = 0, stSpill = 0, stFlush = 0, stTreeClr = 0;
+#endif
+
+  // lane-parallel removal of ranks from the bit-tree (active lanes pass doIt = true). Fire-and-forget: the touched leaf word is
+  // remembered and re-read during the next step (off the critical path); if it is empty then, it is unhooked from the upper levels.
+  auto treeClear = [&]( bool doIt, uint32_t rank ) {
+    if ( doIt ) {
+      atomicAnd( (unsigned long long*)&a.L0[rank >> 6], ~( 1ull << ( rank & 63 ) ) );
+      pendingWord = rank >> 6;
+    }
+    if ( __ballot_sync( FULL, doIt && rank + 1 == gTop ) ) gTopValid = false;
+  };
+  // lane-parallel insertion into the bit-tree; keeps the cached top current
+  auto treeInsert = [&]( bool doIt, uint32_t rank, uint32_t info ) {
+    if ( doIt ) {
+      a.rankEnd[rank] = info;
+      atomicOr( (unsigned long long*)&a.L0[rank >> 6], 1ull << ( rank & 63 ) );
+      lv.set( rank );
+    }
+    const uint32_t mx = __reduce_max_sync( FULL, doIt ? rank + 1 : 0u );
+    if ( mx > gTop && gTopValid ) {  // (an invalid cache is re-read anyway)
+      const int src = __ffs( __ballot_sync( FULL, doIt && rank + 1 == mx ) ) - 1;
+      gTop          = mx;
+      gTopInfo      = __shfl_sync( FULL, info, src );
+    }
+  };
 
   // grows one tree from position `cur` (already marked visited, flip decided) until the queue is empty
   auto grow = [&]( uint32_t cur, bool curFlip ) {
     for ( ;; ) {
-      // ---- phase 1: issue the independent loads
+      // ---- phase 1: the neighbour row of the visited point; the scout re-reads the top of the bit-tree if the cache is stale
       uint2 slot = make_uint2( kInvalid, 0 );
       if ( lane < 16 ) slot = a.rows[size_t( cur ) * 16 + lane];
-      int      leaf = -1;
-      uint64_t w0   = 0;
-      if ( lane == 16 ) {
-        if ( removalPending ) {
-          if ( ( removalOld & ~removalBit ) == 0 ) lv.leafEmptied( removalWord );
-          removalPending = false;
+      uint64_t pendVal = 1;  // leaf word cleared in the previous step: still holding other ranks?
+      if ( pendingWord != kNone ) pendVal = __ldcg( (const unsigned long long*)&a.L0[pendingWord] );
+      if ( !gTopValid ) {
+#ifdef PCC_WALK_STATS
+        ++stRefresh;
+#endif
+        uint32_t found = 0, info = 0;
+        for ( ;; ) {
+          int      leaf = -1;
+          uint64_t w0   = 1;
+          if ( lane == 16 ) {
+            leaf = lv.topLeaf( a.nL4 );
+            if ( leaf >= 0 ) w0 = __ldcg( (const unsigned long long*)&a.L0[leaf] );
+          }
+          const bool stale = __shfl_sync( FULL, int( leaf >= 0 && w0 == 0 ), 16 ) != 0;  // an upper bit still pointing at a drained word
+          if ( stale ) {  // (typically the word of the entry popped in the previous step) unhook it and look again
+            if ( lane == 16 ) lv.leafEmptied( uint32_t( leaf ) );
+            __syncwarp();
+#ifdef PCC_WALK_STATS
+            ++stStale;
+#endif
+            continue;
+          }
+          if ( lane == 16 && leaf >= 0 ) {
+            found = uint32_t( leaf ) * 64 + topBit64( w0 ) + 1;
+            info  = __ldcg( &a.rankEnd[found - 1] );
+          }
+          break;
         }
-        leaf = lv.topLeaf( a.nL4 );
-        if ( leaf >= 0 ) w0 = __ldcg( (const unsigned long long*)&a.L0[leaf] );
+        gTop      = __shfl_sync( FULL, found, 16 );
+        gTopInfo  = __shfl_sync( FULL, info, 16 );
+        gTopValid = true;
       }
-      // ---- phase 2: dependent loads
+      // ---- phase 2: state of the neighbours
       uint32_t old = kVisited;
       if ( lane < 16 && slot.x != kInvalid ) old = __ldcg( &a.best[slot.x] );
-      uint32_t rB = 0, infoB = 0;  // rank + 1 of the scout's find (0 = none)
-      if ( lane == 16 && leaf >= 0 ) {
-        // (w0 cannot be 0: the upper levels are exact at this point)
-        const int b = topBit64( w0 );
-        rB          = uint32_t( leaf ) * 64 + b + 1;
-        infoB       = __ldcg( &a.rankEnd[rB - 1] );
-      }
       // ---- phase 3: queue / improve the frontier entries of the unvisited neighbours
+      if ( pendingWord != kNone ) {  // (no bit was set anywhere since pendVal was read)
+        if ( pendVal == 0 ) lv.leafEmptied( pendingWord );
+        pendingWord = kNone;
+      }
+      __syncwarp();
       const uint32_t r        = slot.y & kRankMask;
       const bool     improved = old != kVisited && ( old == kNone || r > old );
       const bool     flipEnd  = curFlip ? ( slot.y & kRelPos ) != 0 : ( slot.y & kRelNeg ) != 0;  // n_cur(final) . n_j(original) < 0
+      const uint32_t info     = slot.x | ( flipEnd ? 0x80000000u : 0u );
       if ( improved ) {
         a.best[slot.x] = r;
-        a.rankEnd[r]   = slot.x | ( flipEnd ? 0x80000000u : 0u );  // also brings the line into L2 for the later pop
-        prefetchL2( a.rows + size_t( slot.x ) * 16 );                // the row the visit of slot.x will read
+        prefetchL2( a.rows + size_t( slot.x ) * 16 );  // the row the visit of slot.x will read
       }
+      // superseded entries leave the queue: from the hot set if they are there, else from the bit-tree
+      unsigned supers     = __ballot_sync( FULL, improved && old != kNone );
+      bool     clearInTree = false;
+      while ( supers ) {
+        const int      k  = __ffs( supers ) - 1;
+        supers &= supers - 1;
+        const uint32_t o  = __shfl_sync( FULL, old, k ) + 1;
+        const unsigned at = __ballot_sync( FULL, hotRank == o );
+        if ( at ) {
+          if ( lane == __ffs( at ) - 1 ) hotRank = 0;
+        } else if ( lane == k ) {
+          clearInTree = true;
+        }
+      }
+#ifdef PCC_WALK_STATS
+      stTreeClr += __popc( __ballot_sync( FULL, clearInTree ) );
+#endif
+      if ( __ballot_sync( FULL, clearInTree ) ) treeClear( clearInTree, old );
+      // new entries: the largest one may be visited right away; the others go to free hot slots, the overflow to the bit-tree
       const uint32_t myCand = improved ? r + 1 : 0;
-      const uint32_t A      = __reduce_max_sync( 0xffffffffu, myCand );
-      rB                    = __shfl_sync( 0xffffffffu, rB, 16 );
-      if ( A == 0 && rB == 0 ) return;  // queue empty, nothing queued: this tree is complete
-      const bool newWins = A > rB;      // (a superseded scout find always loses: its replacement has a larger rank)
-      // superseded entries leave the queue; a drained leaf word is unhooked from the upper levels right away
-      if ( improved && old != kNone ) {
-        const uint64_t bit = 1ull << ( old & 63 );
-        const uint64_t o   = atomicAnd( (unsigned long long*)&a.L0[old >> 6], ~bit );
-        if ( ( o & ~bit ) == 0 ) lv.leafEmptied( old >> 6 );
+      const uint32_t A      = __reduce_max_sync( FULL, myCand );
+      const uint32_t hotMax = __reduce_max_sync( FULL, hotRank );
+      if ( A == 0 && hotMax == 0 && gTop == 0 ) return;  // nothing queued anywhere: this tree is complete
+      const bool newWins = A > hotMax && A > gTop;
+      const bool toQueue = improved && !( newWins && myCand == A );
+      {
+        const unsigned freeMask = __ballot_sync( FULL, hotRank == 0 );
+        const unsigned newMask  = __ballot_sync( FULL, toQueue );
+        const int      nFree = __popc( freeMask ), nNew = __popc( newMask );
+        // the i-th free slot takes the i-th new entry
+        const int      myFreeIdx = __popc( freeMask & ( ( 1u << lane ) - 1u ) );
+        const int      srcLane   = ( hotRank == 0 && myFreeIdx < nNew ) ? int( __fns( newMask, 0, myFreeIdx + 1 ) ) : 0;
+        const uint32_t inRank = __shfl_sync( FULL, myCand, srcLane ), inInfo = __shfl_sync( FULL, info, srcLane );
+        if ( hotRank == 0 && myFreeIdx < nNew ) hotRank = inRank, hotInfo = inInfo;
+        const int  myNewIdx = __popc( newMask & ( ( 1u << lane ) - 1u ) );
+        const bool spill    = toQueue && myNewIdx >= nFree;
+        if ( nNew > nFree ) treeInsert( spill, r, info );
+#ifdef PCC_WALK_STATS
+        if ( nNew > nFree ) stSpill += nNew - nFree;
+#endif
       }
-      __syncwarp();
-      // new entries enter the queue — except the one that is visited next
-      if ( improved && !( newWins && myCand == A ) ) {
-        atomicOr( (unsigned long long*)&a.L0[r >> 6], 1ull << ( r & 63 ) );
-        lv.set( r );
-      }
+      // ---- pop: the largest of (newest entry, hot set, bit-tree)
       uint32_t next;
       bool     nextFlip;
       if ( newWins ) {
-        const int src = __ffs( __ballot_sync( 0xffffffffu, myCand == A ) ) - 1;
-        next          = __shfl_sync( 0xffffffffu, slot.x, src );
-        nextFlip      = __shfl_sync( 0xffffffffu, int( flipEnd ), src ) != 0;
+#ifdef PCC_WALK_STATS
+        ++stNew;
+#endif
+        const int src = __ffs( __ballot_sync( FULL, myCand == A ) ) - 1;
+        next          = __shfl_sync( FULL, slot.x, src );
+        nextFlip      = __shfl_sync( FULL, int( flipEnd ), src ) != 0;
+      } else if ( hotMax > gTop ) {
+#ifdef PCC_WALK_STATS
+        ++stHot;
+#endif
+        const int      src = __ffs( __ballot_sync( FULL, hotRank == hotMax ) ) - 1;
+        const uint32_t inf = __shfl_sync( FULL, hotInfo, src );
+        if ( lane == src ) hotRank = 0;
+        next = inf & 0x7fffffffu, nextFlip = ( inf >> 31 ) != 0;
       } else {
-        infoB    = __shfl_sync( 0xffffffffu, infoB, 16 );
-        next     = infoB & 0x7fffffffu;
-        nextFlip = ( infoB >> 31 ) != 0;
-        if ( lane == 16 ) {  // take the scout's find out of the queue; the upper levels are fixed at the start of the next step
-          const uint32_t rank = rB - 1;
-          removalBit          = 1ull << ( rank & 63 );
-          removalWord         = rank >> 6;
-          removalOld          = atomicAnd( (unsigned long long*)&a.L0[removalWord], ~removalBit );
-          removalPending      = true;
-        }
+        next = gTopInfo & 0x7fffffffu, nextFlip = ( gTopInfo >> 31 ) != 0;
+#ifdef PCC_WALK_STATS
+        ++stTree;
+#endif
+        treeClear( lane == 16, gTop - 1 );  // invalidates the cache
       }
       if ( lane == 0 ) {
         a.flip[next] = nextFlip ? 1 : 0;
         a.best[next] = kVisited;
+      }
+      // keep room in the hot set: when it is nearly full, the lower-ranked half moves to the bit-tree
+      {
+        const unsigned used = __ballot_sync( FULL, hotRank != 0 );
+        if ( __popc( used ) > 24 ) {
+          const uint32_t mean = __reduce_add_sync( FULL, hotRank >> 5 ) / __popc( used ) << 5;
+          const bool     out  = hotRank != 0 && hotRank <= mean;
+          treeInsert( out, hotRank - 1, hotInfo );
+#ifdef PCC_WALK_STATS
+          stFlush += __popc( __ballot_sync( FULL, out ) );
+#endif
+          if ( out ) hotRank = 0;
+        }
       }
       __threadfence_block();
       __syncwarp();
@@ -302,6 +397,9 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
       grow( seedPos, seedFlip != 0 );
     }
   }
+#ifdef PCC_WALK_STATS
+  if ( lane == 0 ) printf( "walk n=%d popNew=%u popHot=%u popTree=%u refresh=%u stale=%u spill=%u flush=%u treeClear=%u\n", a.n, stNew, stHot, stTree, stRefresh, stStale, stSpill, stFlush, stTreeClr );
+#endif
 }
 
 __global__ void kApplyFlip( double* __restrict__ normals, const uint8_t* __restrict__ flip, const uint32_t* __restrict__ pos, const short4* __restrict__ pts, int n,

@@ -59,3 +59,12 @@ def test_segment_frame(name, oracle, product):
 def test_weight_normal(name, oracle, product):
     xyz = SHAPES[name]()[0]
     assert np.array_equal(product.weight_normal(xyz, 11), oracle.weight_normal(xyz, 11))
+
+
+def test_oriented_normals_full_size_frame(oracle, product):
+    """one frame at the bench size (~0.83 Mpts): the sequential orientation walk must agree with the oracle everywhere"""
+    xyz = synth.figure(scale=0.626, seed=0, frame=1)[0]
+    nbr, _ = oracle.knn(xyz, xyz, 16)
+    want = oracle.normals(xyz, nbr, orient=True)
+    got = product.normals(xyz, 16, orient=True)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
