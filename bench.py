@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--scale", type=float, default=0.626, help="figure scale; 0.626 gives ~0.83 Mpts/frame like longdress_vox10")
     ap.add_argument("--iterations", type=int, default=50, help="iterationCountRefineSegmentation (longdress cfg: 50)")
     ap.add_argument("--ref-frames", type=int, default=32, help="frames per step of the reference arm (one host process per frame, up to the core count)")
-    ap.add_argument("--gofs-in-flight", type=int, default=3, help="GOFs processed concurrently (each on its own context); steps are independent GOFs")
+    ap.add_argument("--gofs-in-flight", type=int, default=1, help="GOFs processed concurrently (each on its own context); steps are independent GOFs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.steps_ref, args.warmup_ref = 1, 0
