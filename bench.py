@@ -170,6 +170,8 @@ def main():
 
     import torch
     dist = None
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)   # NCCL / library chatter must not precede the JSON line on stdout: everything but the result goes to stderr
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -305,7 +307,9 @@ def main():
         sec = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": len(frames[0][0]) / sec / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "reference",
                                "sample": "1 frame of the workload (%.2f Mpts) through the reference's own stages, single thread (CTC --nbThread=1)" % (len(frames[0][0]) / 1e6)}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
