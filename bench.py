@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=32, help="frames per step of the reference arm (one host process per frame, up to the core count)")
     ap.add_argument("--gofs-in-flight", type=int, default=1, help="GOFs processed concurrently (each on its own context); steps are independent GOFs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", default=None, help="write the last GOF's per-frame stage spans (name, start ms, ms) to this JSON file")
     args = ap.parse_args()
     args.steps_ref, args.warmup_ref = 1, 0
 
@@ -252,6 +253,9 @@ def main():
     wall_total = time.perf_counter() - t_begin
     clocks = sampler.finish()
     last_spans, d2h = res[-1][2], res[-1][3]
+    if args.timeline and rank == 0:
+        with open(args.timeline, "w") as fh:
+            json.dump({"host_phase_a_s": res[-1][0], "host_total_s": res[-1][1], "spans": [[n, float(st), float(ms)] for n, ms, st in last_spans]}, fh)
     # device window per GOF (first compute span to last span of any of its frame streams); GOFs overlap, so the job's device time
     # is bounded by the wall clock of the timed region: report the smaller of the two views consistently as wall-based
     dev_each = []

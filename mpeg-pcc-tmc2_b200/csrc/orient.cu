@@ -114,6 +114,11 @@ struct WalkArgs {
 __device__ __forceinline__ int  topBit64( uint64_t w ) { return 63 - __clzll( (long long)w ); }
 __device__ __forceinline__ int  topBit32( uint32_t w ) { return 31 - __clz( int( w ) ); }
 __device__ __forceinline__ void prefetchL2( const void* p ) { asm volatile( "prefetch.global.L2 [%0];" ::"l"( p ) ); }
+// 8-byte asynchronous copy global -> shared (LDGSTS): no destination register, so nothing can stall on it before cpAsyncWait()
+__device__ __forceinline__ void cpAsync8( void* smemDst, const void* g ) {
+  asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" ::"r"( uint32_t( __cvta_generic_to_shared( smemDst ) ) ), "l"( g ) : "memory" );
+}
+__device__ __forceinline__ void cpAsyncWait() { asm volatile( "cp.async.wait_all;" ::: "memory" ); }
 
 // Upper levels of the bit-tree: level l has one bit per word of level l-1. L1 indexes the 64-bit leaf words.
 struct Levels {
@@ -162,8 +167,11 @@ struct Levels {
 // next descent, which keeps the upper levels exact without waiting for an atomic's return value.
 // Dependent chain per visited point in the common case: neighbour row -> best[] of the 16 neighbours.
 __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
-  extern __shared__ uint32_t smem32[];
-  Levels                     lv{ smem32, smem32 + a.nL1, smem32 + a.nL1 + a.nL2, smem32 + a.nL1 + a.nL2 + a.nL3 };
+  extern __shared__ __align__( 16 ) uint32_t smemAll[];
+  uint2* const    rowBuf = reinterpret_cast<uint2*>( smemAll );  // 16 x 8 bytes: landing zone of the next point's neighbour row
+  uint32_t* const stage  = smemAll + 32;                         // 2 x 32 words: hand-over of new entries to free hot slots
+  uint32_t* const smem32 = smemAll + 96;                         // upper levels of the bit-tree
+  Levels          lv{ smem32, smem32 + a.nL1, smem32 + a.nL1 + a.nL2, smem32 + a.nL1 + a.nL2 + a.nL3 };
   const int                  lane = threadIdx.x;
   const unsigned             FULL = 0xffffffffu;
   for ( int i = lane; i < a.nL1 + a.nL2 + a.nL3 + a.nL4; i += 32 ) smem32[i] = 0;
@@ -174,20 +182,24 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
     out[0] = s * a.normals[3 * size_t( orig )], out[1] = s * a.normals[3 * size_t( orig ) + 1], out[2] = s * a.normals[3 * size_t( orig ) + 2];
   };
 
-  uint32_t hotRank = 0, hotInfo = 0;      // per lane: rank + 1 (0 = free slot), end position | flip << 31
-  uint32_t pendingWord = kNone;           // per lane: a leaf word this lane cleared a bit in and has not re-checked yet
-  uint32_t gTop = 0, gTopInfo = 0;        // warp-uniform: cached maximum of the bit-tree (rank + 1, 0 = tree empty)
-  bool     gTopValid = true;              // warp-uniform
+  uint32_t hotRank = 0, hotInfo = 0;  // per lane: rank + 1 (0 = free slot), end position | flip << 31
+  uint32_t pendWord = kNone;          // per lane: leaf word this lane cleared a bit in during the previous step ...
+  uint64_t pendOld = 0, pendBit = 0;  // ... the word's value before the clear (the atomic's return, consumed one step later) and the bit
+  uint32_t gTop = 0;                  // warp-uniform: cached maximum of the bit-tree (rank + 1, 0 = tree empty)
+  uint32_t gTopInfo = 0;              // LANE 16 only: end | flip of that entry (loaded behind the scenes, read when the tree top is popped)
+  bool     gTopValid = true;          // warp-uniform
 #ifdef PCC_WALK_STATS
   unsigned stNew = 0, stHot = 0, stTree = 0, stRefresh = 0, stStale = 0, stSpill = 0, stFlush = 0, stTreeClr = 0;
 #endif
 
-  // lane-parallel removal of ranks from the bit-tree (active lanes pass doIt = true). Fire-and-forget: the touched leaf word is
-  // remembered and re-read during the next step (off the critical path); if it is empty then, it is unhooked from the upper levels.
+  // lane-parallel removal of ranks from the bit-tree (active lanes pass doIt = true; clearing a rank that is not in the tree is
+  // a no-op). The atomic's return value is looked at during the NEXT step, off the critical path: if the word was drained it is
+  // unhooked from the upper levels then (nothing is inserted in between).
   auto treeClear = [&]( bool doIt, uint32_t rank ) {
     if ( doIt ) {
-      atomicAnd( (unsigned long long*)&a.L0[rank >> 6], ~( 1ull << ( rank & 63 ) ) );
-      pendingWord = rank >> 6;
+      pendBit  = 1ull << ( rank & 63 );
+      pendWord = rank >> 6;
+      pendOld  = atomicAnd( (unsigned long long*)&a.L0[pendWord], ~pendBit );
     }
     if ( __ballot_sync( FULL, doIt && rank + 1 == gTop ) ) gTopValid = false;
   };
@@ -206,131 +218,153 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
     }
   };
 
-  // grows one tree from position `cur` (already marked visited, flip decided) until the queue is empty
-  auto grow = [&]( uint32_t cur, bool curFlip ) {
+  // re-reads the largest rank held by the bit-tree (lane 16 descends the shared-memory levels, then reads the leaf word)
+  auto refreshTop = [&]() {
+#ifdef PCC_WALK_STATS
+    ++stRefresh;
+#endif
+    uint32_t found = 0;
     for ( ;; ) {
-      // ---- phase 1: the neighbour row of the visited point; the scout re-reads the top of the bit-tree if the cache is stale
-      uint2 slot = make_uint2( kInvalid, 0 );
-      if ( lane < 16 ) slot = a.rows[size_t( cur ) * 16 + lane];
-      uint64_t pendVal = 1;  // leaf word cleared in the previous step: still holding other ranks?
-      if ( pendingWord != kNone ) pendVal = __ldcg( (const unsigned long long*)&a.L0[pendingWord] );
-      if ( !gTopValid ) {
-#ifdef PCC_WALK_STATS
-        ++stRefresh;
-#endif
-        uint32_t found = 0, info = 0;
-        for ( ;; ) {
-          int      leaf = -1;
-          uint64_t w0   = 1;
-          if ( lane == 16 ) {
-            leaf = lv.topLeaf( a.nL4 );
-            if ( leaf >= 0 ) w0 = __ldcg( (const unsigned long long*)&a.L0[leaf] );
-          }
-          const bool stale = __shfl_sync( FULL, int( leaf >= 0 && w0 == 0 ), 16 ) != 0;  // an upper bit still pointing at a drained word
-          if ( stale ) {  // (typically the word of the entry popped in the previous step) unhook it and look again
-            if ( lane == 16 ) lv.leafEmptied( uint32_t( leaf ) );
-            __syncwarp();
-#ifdef PCC_WALK_STATS
-            ++stStale;
-#endif
-            continue;
-          }
-          if ( lane == 16 && leaf >= 0 ) {
-            found = uint32_t( leaf ) * 64 + topBit64( w0 ) + 1;
-            info  = __ldcg( &a.rankEnd[found - 1] );
-          }
-          break;
-        }
-        gTop      = __shfl_sync( FULL, found, 16 );
-        gTopInfo  = __shfl_sync( FULL, info, 16 );
-        gTopValid = true;
+      int      leaf = -1;
+      uint64_t w0   = 1;
+      if ( lane == 16 ) {
+        leaf = lv.topLeaf( a.nL4 );
+        if ( leaf >= 0 ) w0 = __ldcg( (const unsigned long long*)&a.L0[leaf] );
       }
-      // ---- phase 2: state of the neighbours
-      uint32_t old = kVisited;
-      if ( lane < 16 && slot.x != kInvalid ) old = __ldcg( &a.best[slot.x] );
-      // ---- phase 3: queue / improve the frontier entries of the unvisited neighbours
-      if ( pendingWord != kNone ) {  // (no bit was set anywhere since pendVal was read)
-        if ( pendVal == 0 ) lv.leafEmptied( pendingWord );
-        pendingWord = kNone;
+      const bool stale = __shfl_sync( FULL, int( leaf >= 0 && w0 == 0 ), 16 ) != 0;  // an upper bit still pointing at a drained word
+      if ( stale ) {  // unhook it and look again
+        if ( lane == 16 ) lv.leafEmptied( uint32_t( leaf ) );
+        __syncwarp();
+#ifdef PCC_WALK_STATS
+        ++stStale;
+#endif
+        continue;
       }
+      if ( lane == 16 && leaf >= 0 ) {
+        found    = uint32_t( leaf ) * 64 + topBit64( w0 ) + 1;
+        gTopInfo = __ldcg( &a.rankEnd[found - 1] );
+      }
+      break;
+    }
+    gTop      = __shfl_sync( FULL, found, 16 );
+    gTopValid = true;
+  };
+
+  // grows one tree from position `cur` (already marked visited, flip decided) until the queue is empty.
+  // Priority queue = a 32-entry HOT SET in registers (one entry per lane: the most recently queued edges, which the greedy walk
+  // pops next most of the time) + the bit-tree for everything that spills. A hot entry superseded by a better edge to the same
+  // point is dropped lazily: every lane re-checks best[] of its entry's end at the top of each step (an entry superseded in the
+  // current step is smaller than its successor, so it cannot win before that check); superseded ranks are always cleared in the
+  // bit-tree, where they are if the hot set does not hold them.
+  // Software-pipelined: the point visited next needs only best[] of the 16 neighbours, the hot-set maximum and the cached tree
+  // top; its neighbour row is requested as soon as it is known and the queue upkeep runs while that row is on its way.
+  auto grow = [&]( uint32_t cur, bool curFlip ) {
+    // (the row travels global -> shared by an asynchronous copy: a register load would be waited for at the first copy of its
+    // destination register, which the compiler places right behind the load)
+    if ( lane < 16 ) cpAsync8( rowBuf + lane, a.rows + size_t( cur ) * 16 + lane );
+    for ( ;; ) {
+      cpAsyncWait();
       __syncwarp();
+      const uint2 slot = lane < 16 ? rowBuf[lane] : make_uint2( kInvalid, 0 );
+      __syncwarp();
+      // ---- A: state of the neighbours and of the hot entries' ends (best[] is private to this warp: L1-cached loads)
+      uint32_t old = kVisited, hv = 0;
+      if ( lane < 16 && slot.x != kInvalid ) old = a.best[slot.x];
+      if ( hotRank != 0 ) hv = a.best[hotInfo & 0x7fffffffu];
       const uint32_t r        = slot.y & kRankMask;
       const bool     improved = old != kVisited && ( old == kNone || r > old );
       const bool     flipEnd  = curFlip ? ( slot.y & kRelPos ) != 0 : ( slot.y & kRelNeg ) != 0;  // n_cur(final) . n_j(original) < 0
       const uint32_t info     = slot.x | ( flipEnd ? 0x80000000u : 0u );
-      if ( improved ) {
-        a.best[slot.x] = r;
-        prefetchL2( a.rows + size_t( slot.x ) * 16 );  // the row the visit of slot.x will read
-      }
-      // superseded entries leave the queue: from the hot set if they are there, else from the bit-tree
-      unsigned supers     = __ballot_sync( FULL, improved && old != kNone );
-      bool     clearInTree = false;
-      while ( supers ) {
-        const int      k  = __ffs( supers ) - 1;
-        supers &= supers - 1;
-        const uint32_t o  = __shfl_sync( FULL, old, k ) + 1;
-        const unsigned at = __ballot_sync( FULL, hotRank == o );
-        if ( at ) {
-          if ( lane == __ffs( at ) - 1 ) hotRank = 0;
-        } else if ( lane == k ) {
-          clearInTree = true;
-        }
-      }
-#ifdef PCC_WALK_STATS
-      stTreeClr += __popc( __ballot_sync( FULL, clearInTree ) );
-#endif
-      if ( __ballot_sync( FULL, clearInTree ) ) treeClear( clearInTree, old );
-      // new entries: the largest one may be visited right away; the others go to free hot slots, the overflow to the bit-tree
-      const uint32_t myCand = improved ? r + 1 : 0;
+      const uint32_t myCand   = improved ? r + 1 : 0;
+      if ( hv != hotRank - 1 ) hotRank = 0;  // superseded or visited through another edge (a free slot stays free: hv = 0 != -1)
       const uint32_t A      = __reduce_max_sync( FULL, myCand );
       const uint32_t hotMax = __reduce_max_sync( FULL, hotRank );
       if ( A == 0 && hotMax == 0 && gTop == 0 ) return;  // nothing queued anywhere: this tree is complete
       const bool newWins = A > hotMax && A > gTop;
-      const bool toQueue = improved && !( newWins && myCand == A );
-      {
-        const unsigned freeMask = __ballot_sync( FULL, hotRank == 0 );
-        const unsigned newMask  = __ballot_sync( FULL, toQueue );
-        const int      nFree = __popc( freeMask ), nNew = __popc( newMask );
-        // the i-th free slot takes the i-th new entry
-        const int      myFreeIdx = __popc( freeMask & ( ( 1u << lane ) - 1u ) );
-        const int      srcLane   = ( hotRank == 0 && myFreeIdx < nNew ) ? int( __fns( newMask, 0, myFreeIdx + 1 ) ) : 0;
-        const uint32_t inRank = __shfl_sync( FULL, myCand, srcLane ), inInfo = __shfl_sync( FULL, info, srcLane );
-        if ( hotRank == 0 && myFreeIdx < nNew ) hotRank = inRank, hotInfo = inInfo;
-        const int  myNewIdx = __popc( newMask & ( ( 1u << lane ) - 1u ) );
-        const bool spill    = toQueue && myNewIdx >= nFree;
-        if ( nNew > nFree ) treeInsert( spill, r, info );
-#ifdef PCC_WALK_STATS
-        if ( nNew > nFree ) stSpill += nNew - nFree;
-#endif
-      }
-      // ---- pop: the largest of (newest entry, hot set, bit-tree)
-      uint32_t next;
-      bool     nextFlip;
+      const bool hotWins = !newWins && hotMax > gTop;
+      // ---- B: the point visited next
+      int      src = 16;
+      uint32_t nextInfo;
       if ( newWins ) {
+        src      = __ffs( __ballot_sync( FULL, myCand == A ) ) - 1;
+        nextInfo = __shfl_sync( FULL, info, src );
 #ifdef PCC_WALK_STATS
         ++stNew;
 #endif
-        const int src = __ffs( __ballot_sync( FULL, myCand == A ) ) - 1;
-        next          = __shfl_sync( FULL, slot.x, src );
-        nextFlip      = __shfl_sync( FULL, int( flipEnd ), src ) != 0;
-      } else if ( hotMax > gTop ) {
+      } else if ( hotWins ) {
+        src      = __ffs( __ballot_sync( FULL, hotRank == hotMax ) ) - 1;
+        nextInfo = __shfl_sync( FULL, hotInfo, src );
 #ifdef PCC_WALK_STATS
         ++stHot;
 #endif
-        const int      src = __ffs( __ballot_sync( FULL, hotRank == hotMax ) ) - 1;
-        const uint32_t inf = __shfl_sync( FULL, hotInfo, src );
-        if ( lane == src ) hotRank = 0;
-        next = inf & 0x7fffffffu, nextFlip = ( inf >> 31 ) != 0;
       } else {
-        next = gTopInfo & 0x7fffffffu, nextFlip = ( gTopInfo >> 31 ) != 0;
+        nextInfo = __shfl_sync( FULL, gTopInfo, 16 );
 #ifdef PCC_WALK_STATS
         ++stTree;
 #endif
-        treeClear( lane == 16, gTop - 1 );  // invalidates the cache
       }
-      if ( lane == 0 ) {
+      const uint32_t next     = nextInfo & 0x7fffffffu;
+      const bool     nextFlip = ( nextInfo >> 31 ) != 0;
+      // ---- C: frontier keys of the improved neighbours, the visited mark (one writer per address); then the next row is requested
+      const bool toQueue = improved && !( newWins && lane == src );
+      if ( toQueue ) {
+        a.best[slot.x] = r;
+        prefetchL2( a.rows + size_t( slot.x ) * 16 );  // the row the visit of slot.x will read
+      }
+      if ( newWins ? lane == src : lane == 0 ) {
         a.flip[next] = nextFlip ? 1 : 0;
         a.best[next] = kVisited;
+      }
+      if ( lane < 16 ) cpAsync8( rowBuf + lane, a.rows + size_t( next ) * 16 + lane );
+      // ---- D: queue upkeep. Leaf words drained in the previous step are unhooked before anything is inserted
+      if ( pendWord != kNone ) {
+        if ( ( pendOld & ~pendBit ) == 0 ) lv.leafEmptied( pendWord );
+        pendWord = kNone;
+      }
+      // the popped entry leaves the queue; after a pop from the bit-tree its new top is usually in the same leaf word
+      if ( hotWins ) {
+        if ( lane == src ) hotRank = 0;
+      } else if ( !newWins ) {
+        uint32_t found   = 0;
+        bool     descend = false;
+        if ( lane == 16 ) {
+          const uint32_t rank = gTop - 1;
+          const uint64_t bit  = 1ull << ( rank & 63 );
+          const uint64_t left = atomicAnd( (unsigned long long*)&a.L0[rank >> 6], ~bit ) & ~bit;
+          if ( left != 0 ) {
+            found    = ( rank & ~63u ) + topBit64( left ) + 1;
+            gTopInfo = __ldcg( &a.rankEnd[found - 1] );
+          } else {
+            lv.leafEmptied( rank >> 6 );
+            descend = true;
+          }
+        }
+        gTop = __shfl_sync( FULL, found, 16 );
+        if ( __shfl_sync( FULL, int( descend ), 16 ) ) {
+          __syncwarp();
+          refreshTop();
+        }
+      }
+      __syncwarp();
+      // new entries go to free hot slots (the i-th free slot takes the i-th new entry), the overflow to the bit-tree
+      {
+        const unsigned newMask = __ballot_sync( FULL, toQueue );
+        if ( newMask ) {
+          const unsigned freeMask = __ballot_sync( FULL, hotRank == 0 );
+          const int      nFree = __popc( freeMask ), nNew = __popc( newMask );
+          const unsigned below     = ( 1u << lane ) - 1u;
+          const int      myNewIdx  = __popc( newMask & below );
+          const int      myFreeIdx = __popc( freeMask & below );
+          if ( toQueue ) stage[myNewIdx] = myCand, stage[32 + myNewIdx] = info;
+          __syncwarp();
+          if ( hotRank == 0 && myFreeIdx < nNew ) hotRank = stage[myFreeIdx], hotInfo = stage[32 + myFreeIdx];
+          if ( nNew > nFree ) {
+            treeInsert( toQueue && myNewIdx >= nFree, r, info );
+#ifdef PCC_WALK_STATS
+            stSpill += nNew - nFree;
+#endif
+          }
+        }
       }
       // keep room in the hot set: when it is nearly full, the lower-ranked half moves to the bit-tree
       {
@@ -345,9 +379,21 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
           if ( out ) hotRank = 0;
         }
       }
-      __threadfence_block();
+      // superseded ranks leave the bit-tree (after the inserts: an entry flushed above may be one of them)
+      {
+        const bool sup = improved && old != kNone;
+        if ( __ballot_sync( FULL, sup ) ) {
+          __syncwarp();
+          treeClear( sup, old );
+#ifdef PCC_WALK_STATS
+          stTreeClr += __popc( __ballot_sync( FULL, sup ) );
+#endif
+        }
+      }
+      // (__syncwarp orders the lanes' memory accesses; a __threadfence_block here would also wait for the row requested in C)
       __syncwarp();
-      cur = next, curFlip = nextFlip;
+      if ( !gTopValid ) refreshTop();
+      curFlip = nextFlip;
     }
   };
 
@@ -462,7 +508,7 @@ void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, i
   PCC_CUDA( cudaMemsetAsync( sc.counter, 0, sizeof( unsigned ), s ) );
   kFillU32<<<divUp( n, 256 ), 256, 0, s>>>( sc.best, n, kNone );
   a.L0 = sc.L0, a.best = sc.best, a.flip = sc.flip;
-  const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 + a.nL4 ) * 4;
+  const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 + a.nL4 + 96 ) * 4;
   if ( smemBytes > 200 * 1024 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   {  // the limit is a per-function global: raise it once to the maximum any frame may need (frames run on concurrent host threads)
     static std::once_flag once;
