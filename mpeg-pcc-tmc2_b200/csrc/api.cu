@@ -120,7 +120,7 @@ int pccb200_normals( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int k, int 
     ctx->normals.reserve( 3 * n );
     kdKnn( ctx->tree, ctx->xyz4, n, ctx->tree.vind, k, ctx->nbr, nullptr, ctx->stream );
     computeNormals( ctx->xyz4, ctx->nbr, k, n, ctx->normals, ctx->stream );
-    if ( orientation == 1 ) orientNormals( ctx->orient, ctx->xyz4, ctx->nbr, k, ctx->tree.vind, n, ctx->normals, ctx->stream );
+    if ( orientation == 1 ) orientNormals( ctx->orient, ctx->walkArgs, ctx->xyz4, ctx->nbr, k, ctx->tree.vind, n, ctx->normals, ctx->stream );
     PCC_CUDA( cudaMemcpyAsync( normals, ctx->normals, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
     PCC_CUDA( cudaStreamSynchronize( ctx->stream ) );
     return PCCB200_OK;
@@ -194,7 +194,7 @@ int pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* 
     if ( prm->normal_orientation == 1 ) {
       ProfScope t( pf, "orient", s );
       ctx->orient.prof = pf;
-      orientNormals( ctx->orient, ctx->xyz4, ctx->nbr, k, ctx->tree.vind, n, ctx->normals, s );
+      orientNormals( ctx->orient, ctx->walkArgs, ctx->xyz4, ctx->nbr, k, ctx->tree.vind, n, ctx->normals, s );
     }
     if ( normals ) PCC_CUDA( cudaMemcpyAsync( normals, ctx->normals, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, s ) );
     {

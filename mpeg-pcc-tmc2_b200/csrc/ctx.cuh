@@ -62,6 +62,7 @@ struct pccb200_ctx {
   OrientScratch    orient;
   RefineScratch    refine;
   PatchScratch     patch;
+  DevBuf<unsigned char> walkArgs;  // per-frame arguments of a batched orientation walk
   std::vector<std::unique_ptr<FrameState>> framePool;  // reused by successive GOFs (gof.cu)
   ~pccb200_ctx();
 };

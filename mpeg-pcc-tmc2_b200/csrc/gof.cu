@@ -8,6 +8,9 @@
 #include <algorithm>
 #include <cmath>
 #include <stdexcept>
+#include <condition_variable>
+#include <exception>
+#include <mutex>
 #include <thread>
 
 #include "stages.cuh"
@@ -61,8 +64,40 @@ int forEachFrame( pccb200_gof* g, F&& fn ) {
   return PCCB200_OK;
 }
 
-// a1..a11 for one frame (PCCPatchSegmenter3::compute)
-void segmentFrame( FrameState& fs, const pccb200_seg_params& prm ) {
+// Meeting point of the frame threads of a GOF between the data-parallel part of the orientation and the walks: the last frame to
+// arrive launches the walks of ALL frames as one grid on the context's stream and waits for them; then everybody goes on.
+// (One launch = one hardware queue held for the ~1 s the walks take, instead of one per frame - with every queue occupied by a
+// running walk nothing else could start on the device, e.g. the stages of the next GOF.)
+struct WalkGate {
+  std::mutex                  m;
+  std::condition_variable     cv;
+  int                         expected = 0, arrived = 0;
+  bool                        done = false, failed = false;
+  std::string                 error;
+  std::vector<OrientScratch*> items;
+  void arrive( OrientScratch* item, pccb200_ctx* ctx ) {
+    std::unique_lock<std::mutex> lk( m );
+    if ( item ) items.push_back( item );
+    if ( ++arrived < expected ) {
+      cv.wait( lk, [&]() { return done; } );
+    } else {
+      try {
+        orientWalkBatch( items.data(), int( items.size() ), ctx->walkArgs, &ctx->prof, ctx->stream );
+      } catch ( const CudaError& e ) {
+        char buf[256];
+        snprintf( buf, sizeof( buf ), "orientation walk: CUDA error %d (%s) at %s:%d", int( e.code ), cudaGetErrorString( e.code ), e.file, e.line );
+        failed = true, error = buf;
+        cudaGetLastError();
+      }
+      done = true;
+      cv.notify_all();
+    }
+    if ( failed ) throw std::runtime_error( error );
+  }
+};
+
+// a1..a4 + the data-parallel part of a5 for one frame (PCCPatchSegmenter3::compute)
+void segmentFrameBeforeWalk( FrameState& fs, const pccb200_seg_params& prm ) {
   cudaStream_t s = fs.stream;
   const size_t n = fs.n;
   const int    k = 16;
@@ -91,11 +126,22 @@ void segmentFrame( FrameState& fs, const pccb200_seg_params& prm ) {
     ProfScope t( pf, "normals", s );
     computeNormals( fs.xyz4, fs.nbr, k, n, fs.normals, s );
   }
+  fs.orient.walkSmem = 0;
   if ( prm.normal_orientation == 1 ) {
     ProfScope t( pf, "orient", s );
     fs.orient.prof = pf;
-    orientNormals( fs.orient, fs.xyz4, fs.nbr, k, fs.tree.vind, n, fs.normals, s );
+    orientPrepare( fs.orient, fs.xyz4, fs.nbr, k, fs.tree.vind, n, fs.normals, s );
   }
+}
+
+// ... a5 (the orientation walks of all frames, one launch: WalkGate below) ... then a5's sign application and a6..a11
+void segmentFrameAfterWalk( FrameState& fs, const pccb200_seg_params& prm ) {
+  cudaStream_t s = fs.stream;
+  const size_t n = fs.n;
+  const int    k = 16;
+  Profiler*    pf = &fs.prof;
+  if ( n == 0 ) return;
+  if ( prm.normal_orientation == 1 ) orientFinish( fs.orient, fs.xyz4, n, fs.normals, s );
   {
     ProfScope t( pf, "initial_seg", s );
     initialSegmentation( fs.normals, n, prm.weight_normal, fs.partition, s );
@@ -225,6 +271,7 @@ int runCanvasStages( pccb200_gof* g, int stopAfter ) {
 }
 
 void collectProfiles( pccb200_gof* g ) {
+  g->ctx->prof.collect( g->ctx->stream );  // GOF-level spans (the batched orientation walk)
   for ( auto* fs : g->frames ) {
     fs->prof.collect( fs->stream );
     for ( auto& r : fs->prof.results ) g->ctx->prof.results.push_back( r );
@@ -265,8 +312,19 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
       g->frames.push_back( fs );
     }
     const int minW = prm->geometry_bitdepth_3d > 11 ? 2560 : 1280, minH = 1280;  // minimumImageWidth/Height (cfg/sequence/*_vox11.cfg: 2560)
+    WalkGate gate;
+    gate.expected  = nframes;
     int       rc   = forEachFrame( g, [&]( FrameState& fs, int ) {
-      segmentFrame( fs, g->prm );
+      std::exception_ptr early;
+      try {
+        segmentFrameBeforeWalk( fs, g->prm );
+        PCC_CUDA( cudaStreamSynchronize( fs.stream ) );
+      } catch ( ... ) {
+        early = std::current_exception();  // (this frame still has to show up at the gate, or the others would wait forever)
+      }
+      gate.arrive( early || fs.orient.walkSmem == 0 ? nullptr : &fs.orient, ctx );
+      if ( early ) std::rethrow_exception( early );
+      segmentFrameAfterWalk( fs, g->prm );
       packFrame( fs, g->prm, minW, minH, 2, 1.0 );
     } );
     if ( rc != PCCB200_OK ) {

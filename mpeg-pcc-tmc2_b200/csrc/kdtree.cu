@@ -281,7 +281,6 @@ __global__ void kGatherPts( const short4* __restrict__ pts, const uint32_t* __re
 }
 
 // ------------------------------------------------------------------------------------------- k-NN search
-constexpr int kMaxK     = 16;
 constexpr int kMaxStack = 96;
 
 struct Box6 {

@@ -17,7 +17,9 @@
 // Frames of a GOF run this stage concurrently on separate streams (one resident warp each).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "stages.cuh"
 
@@ -118,7 +120,12 @@ __device__ __forceinline__ void prefetchL2( const void* p ) { asm volatile( "pre
 __device__ __forceinline__ void cpAsync8( void* smemDst, const void* g ) {
   asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" ::"r"( uint32_t( __cvta_generic_to_shared( smemDst ) ) ), "l"( g ) : "memory" );
 }
+__device__ __forceinline__ void cpAsync16( void* smemDst, const void* g ) {  // (.cg: straight from L2, never a stale L1 line)
+  asm volatile( "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"( uint32_t( __cvta_generic_to_shared( smemDst ) ) ), "l"( g ) : "memory" );
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
 __device__ __forceinline__ void cpAsyncWait() { asm volatile( "cp.async.wait_all;" ::: "memory" ); }
+__device__ __forceinline__ void cpAsyncWaitAllButLatest() { asm volatile( "cp.async.wait_group 1;" ::: "memory" ); }
 
 // Upper levels of the bit-tree: level l has one bit per word of level l-1. L1 indexes the 64-bit leaf words.
 struct Levels {
@@ -166,11 +173,15 @@ struct Levels {
 // popped or superseded. Clears of the bit-tree are fire-and-forget: the touched leaf word is remembered and re-read before the
 // next descent, which keeps the upper levels exact without waiting for an atomic's return value.
 // Dependent chain per visited point in the common case: neighbour row -> best[] of the 16 neighbours.
-__global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
+// One CTA (one warp) per frame of the batch: every frame of a GOF walks inside the SAME launch, so the walks hold one hardware
+// queue instead of one each (a long-running kernel blocks whatever is queued behind it on its connection).
+__global__ void __launch_bounds__( 32, 1 ) kWalk( const WalkArgs* __restrict__ batch ) {
+  const WalkArgs a = batch[blockIdx.x];
   extern __shared__ __align__( 16 ) uint32_t smemAll[];
   uint2* const    rowBuf = reinterpret_cast<uint2*>( smemAll );  // 16 x 8 bytes: landing zone of the next point's neighbour row
-  uint32_t* const stage  = smemAll + 32;                         // 2 x 32 words: hand-over of new entries to free hot slots
-  uint32_t* const smem32 = smemAll + 96;                         // upper levels of the bit-tree
+  uint64_t* const pendBuf = reinterpret_cast<uint64_t*>( smemAll + 32 );  // 32 x 16 bytes: re-read leaf words (one pair per lane)
+  uint32_t* const stage  = smemAll + 160;                        // 2 x 32 words: hand-over of new entries to free hot slots
+  uint32_t* const smem32 = smemAll + 224;                        // upper levels of the bit-tree
   Levels          lv{ smem32, smem32 + a.nL1, smem32 + a.nL1 + a.nL2, smem32 + a.nL1 + a.nL2 + a.nL3 };
   const int                  lane = threadIdx.x;
   const unsigned             FULL = 0xffffffffu;
@@ -183,8 +194,7 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
   };
 
   uint32_t hotRank = 0, hotInfo = 0;  // per lane: rank + 1 (0 = free slot), end position | flip << 31
-  uint32_t pendWord = kNone;          // per lane: leaf word this lane cleared a bit in during the previous step ...
-  uint64_t pendOld = 0, pendBit = 0;  // ... the word's value before the clear (the atomic's return, consumed one step later) and the bit
+  uint32_t pendWord = kNone;          // per lane: leaf word this lane cleared a bit in during the previous step, not re-checked yet
   uint32_t gTop = 0;                  // warp-uniform: cached maximum of the bit-tree (rank + 1, 0 = tree empty)
   uint32_t gTopInfo = 0;              // LANE 16 only: end | flip of that entry (loaded behind the scenes, read when the tree top is popped)
   bool     gTopValid = true;          // warp-uniform
@@ -193,13 +203,12 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
 #endif
 
   // lane-parallel removal of ranks from the bit-tree (active lanes pass doIt = true; clearing a rank that is not in the tree is
-  // a no-op). The atomic's return value is looked at during the NEXT step, off the critical path: if the word was drained it is
-  // unhooked from the upper levels then (nothing is inserted in between).
+  // a no-op). Fire-and-forget: the touched leaf word is re-read during the NEXT step by an asynchronous copy, off the critical
+  // path; if it was drained it is unhooked from the upper levels then (nothing is inserted in between).
   auto treeClear = [&]( bool doIt, uint32_t rank ) {
     if ( doIt ) {
-      pendBit  = 1ull << ( rank & 63 );
       pendWord = rank >> 6;
-      pendOld  = atomicAnd( (unsigned long long*)&a.L0[pendWord], ~pendBit );
+      atomicAnd( (unsigned long long*)&a.L0[pendWord], ~( 1ull << ( rank & 63 ) ) );
     }
     if ( __ballot_sync( FULL, doIt && rank + 1 == gTop ) ) gTopValid = false;
   };
@@ -267,6 +276,8 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
       __syncwarp();
       const uint2 slot = lane < 16 ? rowBuf[lane] : make_uint2( kInvalid, 0 );
       __syncwarp();
+      if ( pendWord != kNone ) cpAsync16( pendBuf + 2 * lane, a.L0 + ( pendWord & ~1u ) );
+      cpAsyncCommit();
       // ---- A: state of the neighbours and of the hot entries' ends (best[] is private to this warp: L1-cached loads)
       uint32_t old = kVisited, hv = 0;
       if ( lane < 16 && slot.x != kInvalid ) old = a.best[slot.x];
@@ -316,9 +327,11 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( WalkArgs a ) {
         a.best[next] = kVisited;
       }
       if ( lane < 16 ) cpAsync8( rowBuf + lane, a.rows + size_t( next ) * 16 + lane );
+      cpAsyncCommit();
       // ---- D: queue upkeep. Leaf words drained in the previous step are unhooked before anything is inserted
+      cpAsyncWaitAllButLatest();
       if ( pendWord != kNone ) {
-        if ( ( pendOld & ~pendBit ) == 0 ) lv.leafEmptied( pendWord );
+        if ( pendBuf[2 * lane + ( pendWord & 1u )] == 0 ) lv.leafEmptied( pendWord );
         pendWord = kNone;
       }
       // the popped entry leaves the queue; after a pop from the bit-tree its new top is usually in the same leaf word
@@ -478,8 +491,11 @@ __global__ void kFillU32( uint32_t* p, size_t n, uint32_t v ) {
 
 }  // namespace
 
-void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
+static_assert( sizeof( WalkArgs ) <= sizeof( OrientScratch::walkArgs ), "OrientScratch::walkArgs too small" );
+
+void orientPrepare( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
                     cudaStream_t s ) {
+  sc.walkSmem = 0;
   if ( n == 0 ) return;
   if ( k > 16 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   const size_t E = n * 16;
@@ -507,27 +523,61 @@ void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, i
   PCC_CUDA( cudaMemsetAsync( sc.flip, 0, n, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.counter, 0, sizeof( unsigned ), s ) );
   kFillU32<<<divUp( n, 256 ), 256, 0, s>>>( sc.best, n, kNone );
+  PCC_LAUNCH_CHECK();
   a.L0 = sc.L0, a.best = sc.best, a.flip = sc.flip;
-  const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 + a.nL4 + 96 ) * 4;
+  const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 + a.nL4 + 224 ) * 4;
   if ( smemBytes > 200 * 1024 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
-  {  // the limit is a per-function global: raise it once to the maximum any frame may need (frames run on concurrent host threads)
+  memcpy( sc.walkArgs, &a, sizeof( a ) );
+  sc.walkSmem = smemBytes;
+}
+
+void orientWalkBatch( OrientScratch* const* frames, int count, DevBuf<unsigned char>& devArgs, Profiler* prof, cudaStream_t s ) {
+  std::vector<WalkArgs> args;
+  size_t                smem = 0;
+  for ( int i = 0; i < count; ++i )
+    if ( frames[i] && frames[i]->walkSmem ) {
+      WalkArgs a;
+      memcpy( &a, frames[i]->walkArgs, sizeof( a ) );
+      args.push_back( a );
+      smem = std::max( smem, frames[i]->walkSmem );
+    }
+  if ( args.empty() ) return;
+  {  // the limit is a per-function global: raise it once to the maximum any frame may need
     static std::once_flag once;
     cudaError_t           err = cudaSuccess;
     std::call_once( once, [&]() { err = cudaFuncSetAttribute( kWalk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 ); } );
     PCC_CUDA( err );
   }
+  devArgs.reserve( args.size() * sizeof( WalkArgs ) );
+  PCC_CUDA( cudaMemcpyAsync( devArgs.p, args.data(), args.size() * sizeof( WalkArgs ), cudaMemcpyHostToDevice, s ) );
   {
-    ProfScope t( sc.prof, "orient_walk", s );
-    kWalk<<<1, 32, smemBytes, s>>>( a );
+    ProfScope t( prof, "orient_walk", s );
+    kWalk<<<unsigned( args.size() ), 32, smem, s>>>( reinterpret_cast<const WalkArgs*>( devArgs.p ) );
     PCC_LAUNCH_CHECK();
   }
-  // The walk runs for a long time on one warp. Nothing that depends on it is enqueued until it has finished: a dependent
-  // launch waiting at the head of a hardware queue would stall unrelated kernels of other frames' streams that share the
-  // queue (CUDA_DEVICE_MAX_CONNECTIONS queues for all streams). The per-frame host thread simply waits here.
-  PCC_CUDA( cudaStreamSynchronize( s ) );
+  // The walks run for a long time on one warp each. The host waits BLOCKING (sleeping): nothing that depends on them is
+  // enqueued before they have finished, and no thread spins on the driver meanwhile.
+  cudaEvent_t done;
+  PCC_CUDA( cudaEventCreateWithFlags( &done, cudaEventBlockingSync | cudaEventDisableTiming ) );
+  cudaError_t err = cudaEventRecord( done, s );
+  if ( err == cudaSuccess ) err = cudaEventSynchronize( done );
+  cudaEventDestroy( done );
+  PCC_CUDA( err );
+}
+
+void orientFinish( OrientScratch& sc, const short4* pts, size_t n, double* normals, cudaStream_t s ) {
+  if ( n == 0 ) return;
   kApplyFlip<<<divUp( n, 256 ), 256, 0, s>>>( normals, sc.flip, sc.pos, pts, int( n ), sc.counter );
   kNegateIfMajority<<<divUp( 3 * n, 256 ), 256, 0, s>>>( normals, int( n ), sc.counter );
   PCC_LAUNCH_CHECK();
+}
+
+void orientNormals( OrientScratch& sc, DevBuf<unsigned char>& devArgs, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n,
+                    double* normals, cudaStream_t s ) {
+  orientPrepare( sc, pts, nbr, k, vind, n, normals, s );
+  OrientScratch* one = &sc;
+  orientWalkBatch( &one, 1, devArgs, sc.prof, s );
+  orientFinish( sc, pts, n, normals, s );
 }
 
 }  // namespace pccb200

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__( 32 * kAdjWarps )
 }
 
 // ---- voxel state -------------------------------------------------------------------------------------
+constexpr uint32_t kNoEntry = 0xFFFFFFFFu;  // work-list slot reserved but not written yet
 struct VoxState {
   uint16_t* score;  // V x 6 (stored as 8 x u16 = 16 B rows)
   uint8_t*  edge;
@@ -232,10 +233,14 @@ struct VoxState {
 };
 
 // recount histogram; apply INDIRECT marks; re-derive class/PPI for dirty voxels (updateScores)
+// Also resets the sweep's work list (entries to the "not written yet" sentinel, the three control words to 0).
 __global__ void kRecount( VoxState st, const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
-                          const uint32_t* __restrict__ idsSorted, const uint8_t* __restrict__ partition, int V, int initialise ) {
+                          const uint32_t* __restrict__ idsSorted, const uint8_t* __restrict__ partition, int V, int initialise,
+                          uint32_t* __restrict__ list, unsigned* __restrict__ ctl ) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( v < 3 ) ctl[v] = 0;
   if ( v >= V ) return;
+  list[v] = kNoEntry;
   uint16_t       sc[6] = {0, 0, 0, 0, 0, 0};
   const uint32_t s = voxStart[v], c = voxCount[v];
   for ( uint32_t j = 0; j < c; ++j ) ++sc[partition[idsSorted[s + j]]];
@@ -282,54 +287,76 @@ __global__ void kInitialActive( VoxState st, int V, uint32_t* __restrict__ list,
   }
 }
 
-// smooth[v] = sum of neighbour histograms (uint16 wrap-around like ScoresVector_t), top = first arg-max.
-// One warp per listed voxel; then the 2nd voxel classification: mark NO_EDGE neighbours whose PPI differs,
-// and activate those with a larger index for this very sweep.
+// smooth[v] = sum of neighbour histograms (uint16 wrap-around like ScoresVector_t), top = first arg-max; then the 2nd voxel
+// classification: mark NO_EDGE neighbours whose PPI differs, and activate those with a larger index for this very sweep.
+// ONE launch per sweep: a persistent kernel over a growing work list. ctl[0] = entries reserved (kInitialActive's + those
+// activated here), ctl[1] = next ticket, ctl[2] = entries finished. A warp takes a ticket, waits until that list slot is written
+// (or until every reserved entry is finished: nothing can be appended any more) and processes it; the result does not depend on
+// the processing order (a voxel is only ever activated by a smaller index, smoothing reads sweep-constant scores).
+__device__ __forceinline__ unsigned ldVolatile( const unsigned* p ) { return *reinterpret_cast<const volatile unsigned*>( p ); }
 __global__ void __launch_bounds__( 128 )
-    kSmoothAndMark( VoxState st, const uint32_t* __restrict__ list, unsigned from, unsigned to, const uint32_t* __restrict__ adjOff,
+    kSmoothAndMark( VoxState st, uint32_t* __restrict__ list, unsigned* __restrict__ ctl, const uint32_t* __restrict__ adjOff,
                     const uint32_t* __restrict__ adjLen, const uint32_t* __restrict__ adjData, const uint32_t* __restrict__ nearData,
-                    const uint8_t* __restrict__ nearLen, uint16_t* __restrict__ smooth, uint32_t* __restrict__ listOut, unsigned* __restrict__ count ) {
-  const unsigned w    = from + ( blockIdx.x * blockDim.x + threadIdx.x ) / 32;
-  const int      lane = threadIdx.x & 31;
-  if ( w >= to ) return;
-  const uint32_t v   = list[w];
-  const uint32_t off = adjOff[v], len = adjLen[v];
-  uint32_t       s[6] = {0, 0, 0, 0, 0, 0};
-  for ( uint32_t i = lane; i < len; i += 32 ) {
-    const uint4 r = *reinterpret_cast<const uint4*>( st.score + size_t( adjData[off + i] ) * 8 );
-    s[0] += r.x & 0xffff, s[1] += r.x >> 16, s[2] += r.y & 0xffff, s[3] += r.y >> 16, s[4] += r.z & 0xffff, s[5] += r.z >> 16;
-  }
-#pragma unroll
-  for ( int k = 0; k < 6; ++k ) s[k] = __reduce_add_sync( 0xffffffffu, s[k] ) & 0xffffu;
-  int top = 0;
-#pragma unroll
-  for ( int k = 1; k < 6; ++k )
-    if ( s[k] > s[top] ) top = k;
-  if ( lane < 6 ) smooth[size_t( v ) * 8 + lane] = uint16_t( s[lane] );
-  if ( lane < nearLen[v] ) {
-    const uint32_t o = nearData[size_t( v ) * kMaxNear + lane];
-    if ( st.edge[o] == NO_EDGE && st.ppi[o] != top ) {
-      st.mark[o] = 1;
-      if ( o > v ) {
-        // byte-granular test-and-set on the active flags
-        unsigned* word = reinterpret_cast<unsigned*>( st.active ) + ( o >> 2 );
-        const unsigned bit = 1u << ( 8 * ( o & 3 ) );
-        const unsigned old = atomicOr( word, bit );
-        if ( !( old & bit ) ) listOut[atomicAdd( count, 1u )] = o;
+                    const uint8_t* __restrict__ nearLen, uint16_t* __restrict__ smooth ) {
+  const int lane = threadIdx.x & 31;
+  for ( ;; ) {
+    unsigned w = 0;
+    if ( lane == 0 ) w = atomicAdd( &ctl[1], 1u );
+    w          = __shfl_sync( 0xffffffffu, w, 0 );
+    uint32_t v = kNoEntry;
+    if ( lane == 0 ) {
+      for ( ;; ) {
+        const unsigned c0 = ldVolatile( &ctl[0] );
+        if ( w < c0 ) {
+          while ( ( v = ldVolatile( &list[w] ) ) == kNoEntry ) __nanosleep( 20 );
+          break;
+        }
+        const unsigned done = ldVolatile( &ctl[2] );
+        if ( done == c0 && ldVolatile( &ctl[0] ) == c0 ) break;  // quiescent: all reserved entries finished, none in flight
+        __nanosleep( 100 );
       }
     }
+    v = __shfl_sync( 0xffffffffu, v, 0 );
+    if ( v == kNoEntry ) return;
+    const uint32_t off = adjOff[v], len = adjLen[v];
+    uint32_t       s[6] = {0, 0, 0, 0, 0, 0};
+    for ( uint32_t i = lane; i < len; i += 32 ) {
+      const uint4 r = *reinterpret_cast<const uint4*>( st.score + size_t( adjData[off + i] ) * 8 );
+      s[0] += r.x & 0xffff, s[1] += r.x >> 16, s[2] += r.y & 0xffff, s[3] += r.y >> 16, s[4] += r.z & 0xffff, s[5] += r.z >> 16;
+    }
+#pragma unroll
+    for ( int k = 0; k < 6; ++k ) s[k] = __reduce_add_sync( 0xffffffffu, s[k] ) & 0xffffu;
+    int top = 0;
+#pragma unroll
+    for ( int k = 1; k < 6; ++k )
+      if ( s[k] > s[top] ) top = k;
+    if ( lane < 6 ) smooth[size_t( v ) * 8 + lane] = uint16_t( s[lane] );
+    if ( lane < nearLen[v] ) {
+      const uint32_t o = nearData[size_t( v ) * kMaxNear + lane];
+      if ( st.edge[o] == NO_EDGE && st.ppi[o] != top ) {
+        st.mark[o] = 1;
+        if ( o > v ) {
+          // byte-granular test-and-set on the active flags
+          unsigned* word = reinterpret_cast<unsigned*>( st.active ) + ( o >> 2 );
+          const unsigned bit = 1u << ( 8 * ( o & 3 ) );
+          const unsigned old = atomicOr( word, bit );
+          if ( !( old & bit ) ) {
+            const unsigned at = atomicAdd( &ctl[0], 1u );
+            *reinterpret_cast<volatile uint32_t*>( &list[at] ) = o;
+          }
+        }
+      }
+    }
+    __threadfence();  // the entries appended above are reserved (and written) before this one counts as finished
+    __syncwarp();
+    if ( lane == 0 ) atomicAdd( &ctl[2], 1u );
   }
 }
 
-// relabel the points of every processed voxel (one warp per voxel, one lane per point)
-__global__ void __launch_bounds__( 128 )
-    kRelabel( VoxState st, const uint32_t* __restrict__ list, unsigned total, const uint16_t* __restrict__ smooth,
+// relabel the points of one processed voxel (one warp per voxel, one lane per point)
+__device__ __forceinline__ void relabelVoxel( VoxState st, uint32_t v, int lane, const uint16_t* __restrict__ smooth,
               const double* __restrict__ weight, const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
               const uint32_t* __restrict__ idsSorted, const double* __restrict__ normals, uint8_t* __restrict__ partition ) {
-  const unsigned w    = ( blockIdx.x * blockDim.x + threadIdx.x ) / 32;
-  const int      lane = threadIdx.x & 31;
-  if ( w >= total ) return;
-  const uint32_t v = list[w];
   uint8_t        edgeHere = st.edge[v];
   if ( edgeHere == NO_EDGE ) edgeHere = INDIRECT_EDGE;  // activated during this sweep
   uint16_t s[6];
@@ -358,6 +385,16 @@ __global__ void __launch_bounds__( 128 )
     partition[p] = uint8_t( best );
   }
   if ( lane == 0 ) st.dirty[v] = 1;
+}
+
+// every voxel of the sweep's work list (its length is read on the device)
+__global__ void __launch_bounds__( 128 )
+    kRelabel( VoxState st, const uint32_t* __restrict__ list, const unsigned* __restrict__ ctl, const uint16_t* __restrict__ smooth,
+              const double* __restrict__ weight, const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
+              const uint32_t* __restrict__ idsSorted, const double* __restrict__ normals, uint8_t* __restrict__ partition ) {
+  const int      lane  = threadIdx.x & 31;
+  const unsigned total = ctl[0], nWarps = gridDim.x * ( blockDim.x / 32 );
+  for ( unsigned w = ( blockIdx.x * blockDim.x + threadIdx.x ) / 32; w < total; w += nWarps ) relabelVoxel( st, list[w], lane, smooth, weight, voxStart, voxCount, idsSorted, normals, partition );
 }
 
 std::vector<int> makeOffsets( int r2 ) {
@@ -472,27 +509,17 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
   PCC_CUDA( cudaMemsetAsync( sc.mark, 0, V, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.dirty, 0, V, s ) );
   VoxState st{ sc.score, sc.edge, sc.ppi, sc.dirty, sc.mark, sc.active };
-  kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 1 );
+  sc.count.reserve( 4 );
+  unsigned* const ctl = sc.count;
+  kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 1, sc.list, ctl );
+  // Four launches per sweep and no host round trip: the sweep's work list lives on the device (see kSmoothAndMark).
   const int iterations = std::max( 1, prm.iteration_count_refine );
+  const int sweepCtas  = int( std::min<size_t>( divUp( V, 4 ), 148 * 4 ) );
   for ( int it = 0; it < iterations; ++it ) {
-    PCC_CUDA( cudaMemsetAsync( sc.count, 0, sizeof( unsigned ), s ) );
-    kInitialActive<<<divUp( V, 256 ), 256, 0, s>>>( st, V, sc.list, sc.count );
-    unsigned from = 0, to = 0;
-    PCC_CUDA( cudaMemcpyAsync( &to, sc.count, sizeof( unsigned ), cudaMemcpyDeviceToHost, s ) );
-    PCC_CUDA( cudaStreamSynchronize( s ) );
-    while ( to > from ) {
-      kSmoothAndMark<<<divUp( size_t( to - from ) * 32, 128 ), 128, 0, s>>>( st, sc.list, from, to, sc.adjOff, sc.adjLen, sc.adjData,
-                                                                           sc.nearData, sc.nearLen, sc.smooth, sc.list, sc.count );
-      PCC_LAUNCH_CHECK();
-      from = to;
-      PCC_CUDA( cudaMemcpyAsync( &to, sc.count, sizeof( unsigned ), cudaMemcpyDeviceToHost, s ) );
-      PCC_CUDA( cudaStreamSynchronize( s ) );
-    }
-    if ( to > 0 ) {
-      kRelabel<<<divUp( size_t( to ) * 32, 128 ), 128, 0, s>>>( st, sc.list, to, sc.smooth, sc.weight, sc.voxStart, sc.voxCount,
-                                                               sc.idsSorted, normals, partition );
-    }
-    kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 0 );
+    kInitialActive<<<divUp( V, 256 ), 256, 0, s>>>( st, V, sc.list, ctl );
+    kSmoothAndMark<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.smooth );
+    kRelabel<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.smooth, sc.weight, sc.voxStart, sc.voxCount, sc.idsSorted, normals, partition );
+    kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 0, sc.list, ctl );
     PCC_LAUNCH_CHECK();
   }
 }

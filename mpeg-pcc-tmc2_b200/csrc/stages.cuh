@@ -17,9 +17,18 @@ struct OrientScratch {
   DevBuf<uint8_t>  flip, cubTmp;
   DevBuf<unsigned> counter;
   Profiler*        prof = nullptr;
+  alignas( 8 ) unsigned char walkArgs[160];  // the frame's walk arguments, filled by orientPrepare (opaque here)
+  size_t walkSmem = 0;                       // dynamic shared memory of its walk (0: nothing to walk)
 };
-void orientNormals( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
+// Three steps, so that the walks of all frames of a GOF can share one launch: data-parallel preparation on the frame's stream,
+// the walks of a batch of prepared frames (blocks the calling host thread until they are done), sign application.
+void orientPrepare( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
                     cudaStream_t s );
+void orientWalkBatch( OrientScratch* const* frames, int count, DevBuf<unsigned char>& devArgs, Profiler* prof, cudaStream_t s );
+void orientFinish( OrientScratch& sc, const short4* pts, size_t n, double* normals, cudaStream_t s );
+// all three for one frame
+void orientNormals( OrientScratch& sc, DevBuf<unsigned char>& devArgs, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n,
+                    double* normals, cudaStream_t s );
 
 // refine.cu
 struct RefineScratch {
