@@ -37,12 +37,31 @@ METRIC = "Mpoints/s patch-gen+image-formation, longdress_vox10, 1/2/4/8 GPU"
 HANDOFF = (2, 4, 5, 13, 14)  # products handed to the video codec: OM video, geometry D0/D1, padded attribute T0/T1
 
 
-def make_frames(count, scale, seed=0, distinct=8):
+def pinned(shape, dtype):
+    """numpy array over page-locked host memory (torch owns the allocation): H2D / D2H copies run at PCIe speed, no staging"""
+    import torch
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    t = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    a = t.numpy()[:n].view(dtype).reshape(shape)
+    _PINNED.append(t)
+    return a
+
+
+_PINNED = []
+
+
+def make_frames(count, scale, seed=0, distinct=8, pin=False):
     import synth
     base = []
     for f in range(min(count, distinct)):
         xyz, rgb = synth.figure(scale=scale, seed=seed, frame=f)
-        base.append((np.ascontiguousarray(xyz), np.ascontiguousarray(rgb)))
+        xyz, rgb = np.ascontiguousarray(xyz), np.ascontiguousarray(rgb)
+        if pin:
+            px, pc = pinned(xyz.shape, xyz.dtype), pinned(rgb.shape, rgb.dtype)
+            px[...], pc[...] = xyz, rgb
+            xyz, rgb = px, pc
+        base.append((xyz, rgb))
     return [base[f % len(base)] for f in range(count)]
 
 
@@ -79,6 +98,14 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """cores this process may run on (the box's cgroup / affinity mask, not the machine's socket count)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -101,14 +128,14 @@ def config(args, npts, frames_per_rank, world):
             "stages": "a1-a26: kd-tree, k-NN16, PCA normals, spanning-tree orientation, initial + grid-refined segmentation, patch segmentation, "
                       "packing, occupancy/geometry images + dilation, generatePointCloud, colour transfer, attribute images, push-pull padding",
             "excluded": "ply load, videoEncoder.compress x3, post-processing, bitstream (as in BASELINE.md §4)",
-            "frames_in_flight": frames_per_rank * max(1, min(args.gofs_in_flight, args.steps)), "gofs_in_flight": max(1, min(args.gofs_in_flight, args.steps)), "host_cores": os.cpu_count(), "parallelism": "frames of a GOF sharded over %d GPU(s)" % world,
+            "frames_in_flight": frames_per_rank * max(1, min(args.gofs_in_flight, args.steps)), "gofs_in_flight": max(1, min(args.gofs_in_flight, args.steps)), "host_cores": host_cores(), "parallelism": "frames of a GOF sharded over %d GPU(s)" % world,
             "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2"}
 
 
 def run_reference(args, frames, prm):
     """--impl reference: the reference's own CPU implementation (oracle/_ref, TBB off) on the host cores, one frame per process."""
     import multiprocessing as mp
-    cores = max(1, min(len(frames), os.cpu_count() or 1, args.ref_frames))
+    cores = max(1, min(len(frames), host_cores(), args.ref_frames))
     work = frames[:cores]
     ctx = mp.get_context("fork")
 
@@ -144,16 +171,17 @@ def run_reference(args, frames, prm):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frames per step and GPU (a GOF is 32 frames)")
     ap.add_argument("--scale", type=float, default=0.626, help="figure scale; 0.626 gives ~0.83 Mpts/frame like longdress_vox10")
     ap.add_argument("--iterations", type=int, default=50, help="iterationCountRefineSegmentation (longdress cfg: 50)")
     ap.add_argument("--ref-frames", type=int, default=32, help="frames per step of the reference arm (one host process per frame, up to the core count)")
-    ap.add_argument("--gofs-in-flight", type=int, default=1, help="GOFs processed concurrently (each on its own context); steps are independent GOFs")
+    ap.add_argument("--gofs-in-flight", type=int, default=6, help="GOFs processed concurrently (each on its own context); steps are independent GOFs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", default=None, help="write the last GOF's per-frame stage spans (name, start ms, ms) to this JSON file")
+    ap.add_argument("--scratch-sets", type=int, default=24, help="scratch sets of the device pool = frames inside the data-parallel stage groups at once")
     args = ap.parse_args()
     args.steps_ref, args.warmup_ref = 1, 0
 
@@ -177,10 +205,11 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
-    frames = make_frames(args.frames, args.scale, seed=rank)
+    frames = make_frames(args.frames, args.scale, seed=rank, pin=True)
     lanes = max(1, min(args.gofs_in_flight, args.steps))          # GOFs in flight: one library context (streams + buffers) each
     prods = [bindings.Product(local) for _ in range(lanes)]
     prod = prods[0]
+    prod.lib.pccb200_set_scratch_sets(local, args.scratch_sets)
     # axis weights come from frame 0 of the GOF (rank 0's first frame); every rank needs the same three doubles
     w = torch.tensor(prod.weight_normal(frames[0][0], 11), dtype=torch.float64)
     if dist is not None:
@@ -196,22 +225,32 @@ def main():
     def phase_a(lane):
         """a1..a13 of one GOF: segmentation (incl. the orientation walk) + packing"""
         t0 = time.perf_counter()
-        return bindings.ProductGof(prods[lane], frames, prm, 4), t0
+        g = bindings.ProductGof(prods[lane], frames, prm, 4)
+        return g, (t0, time.perf_counter())
 
     def phase_b(lane, g, t0, W, H):
         """a16..a26 + hand-off: images, reconstruction, colour, attribute images; D2H of every frame the codec would receive"""
         p, outbuf = prods[lane], outbufs[lane]
+        t0, ta = t0
         g.resume(W, H, 0)
         t1 = time.perf_counter()
         nbytes = 0
         for f in range(len(frames)):
             for what in HANDOFF:
-                outbuf[(f, what)] = g.fetch(f, what, outbuf.get((f, what)))
+                cnt = g.count(f, what)
+                if (f, what) not in outbuf or outbuf[(f, what)].size != cnt:
+                    outbuf[(f, what)] = pinned((cnt,), bindings.GOF_DTYPES[what])
+                g.fetch(f, what, outbuf[(f, what)])
                 nbytes += outbuf[(f, what)].nbytes
         t2 = time.perf_counter()
         spans = p.profile_read()
         g.free()
+        host_phases.append((ta - t0, t1 - ta, t2 - t1, time.perf_counter() - t0))
+        gof_log.append((lane, t0, ta, t1, t2, time.perf_counter()))
         return t1 - t0, t2 - t0, spans, nbytes
+
+    gof_log = []       # per GOF: lane, absolute times of start / packed / resumed / fetched / freed
+    host_phases = []   # per GOF: seconds in encode_gof(stop_after=1), all-reduce + resume, fetch, whole lane cycle
 
     def in_threads(fn, count):
         out = [None] * count
@@ -266,14 +305,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    warm = max(args.warmup, lanes)   # every context (lane) must have allocated its buffers before the timed region
-    t_w = time.perf_counter()
+    warm = max(args.warmup, 2 * lanes)   # every context (lane) allocates its buffers in its first GOF; its second one runs warm
     wres = run_steps(warm)
-    if lanes > 1:   # steady-state spacing of GOF starts: one GOF latency / lanes
-        stagger[0] = float(np.median([e for _, e, _, _ in wres])) / lanes
+    if lanes > 1:   # steady-state spacing of GOF starts: latency of one (warm) GOF / lanes
+        stagger[0] = float(np.min([e for _, e, _, _ in wres])) / lanes
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
+    del host_phases[:]
+    del gof_log[:]
     t_begin = time.perf_counter()
     res = run_steps(args.steps)
     barrier()
@@ -323,6 +363,8 @@ def main():
                      "note": "sequential spanning-tree walk, one warp per frame, all frames of a GOF in one launch: latency-bound by construction"},
         "clocks": clocks,
         "gof_device_window_ms": [round(x * 1e3, 1) for x in dev_each],
+        "gof_log_ms": [[g[0]] + [round((x - t_begin) * 1e3) for x in g[1:]] for g in sorted(gof_log, key=lambda g: g[1])],
+        "host_ms_per_gof": dict(zip(("segment_and_pack", "resume", "fetch", "cycle"), (round(float(np.median(c)) * 1e3, 1) for c in zip(*host_phases)))),
         "gpu_mem_used_gb": round((torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 2**30, 1),
     }
     counts_path = os.path.join(ROOT, "profiles", "launch_counts.json")

@@ -84,6 +84,11 @@ int         pccb200_create( int device, pccb200_ctx** out );
 void        pccb200_destroy( pccb200_ctx* ctx );
 const char* pccb200_last_error( const pccb200_ctx* ctx );
 const char* pccb200_version( void );
+/* Device memory policy of the GOF entry points. A frame keeps ~0.3 GB (0.83 Mpts) while its orientation walk runs; the ~1.2 GB
+ * of scratch the data-parallel stages before and after the walk need is leased from a per-device pool shared by all contexts
+ * of the process. `count` (>= 1) bounds the number of scratch sets, i.e. of frames inside those stages at the same time
+ * (default 24, or the environment variable PCCB200_SCRATCH_SETS). Returns the previous bound, or a negative pccb200_status. */
+int         pccb200_set_scratch_sets( int device, int count );
 
 /* Per-stage device timing (CUDA events on the launching stream). While enabled, every entry point appends one
  * (name, milliseconds) record per stage and frame; read returns and clears them. names: capacity x 32 chars; start_ms

@@ -25,6 +25,10 @@ int pccb200_create( int device, pccb200_ctx** out ) {
     cudaGetLastError();
     return PCCB200_ERR_NO_DEVICE;  // no CPU fallback by design
   }
+  // host threads wait for the device sleeping, not spinning (one thread per frame in flight: far more threads than cores);
+  // best effort - the explicit waits of the library (streamWait) block regardless
+  if ( !spinWaits() && cudaSetDevice( device ) == cudaSuccess ) cudaSetDeviceFlags( cudaDeviceScheduleBlockingSync );
+  cudaGetLastError();
   pccb200_ctx* c = new ( std::nothrow ) pccb200_ctx();
   if ( !c ) return PCCB200_ERR_CUDA;
   c->device = device;
@@ -69,6 +73,11 @@ int pccb200_profile_read( pccb200_ctx* ctx, char* names, float* ms, float* start
   return PCCB200_OK;
 }
 
+int pccb200_set_scratch_sets( int device, int count ) {
+  if ( device < 0 || count < 1 ) return PCCB200_ERR_BAD_ARG;
+  return setFrameScratchSets( device, count );
+}
+
 const char* pccb200_last_error( const pccb200_ctx* ctx ) { return ctx ? ctx->lastError.c_str() : "null context"; }
 
 int pccb200_knn( pccb200_ctx* ctx, const int16_t* xyz, size_t n, const int16_t* q, size_t nq, int k, uint32_t* idx, float* dist2 ) {
@@ -93,7 +102,7 @@ int pccb200_knn( pccb200_ctx* ctx, const int16_t* xyz, size_t n, const int16_t* 
     }
     PCC_CUDA( cudaMemcpyAsync( idx, ctx->nbr, nq * k * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx->stream ) );
     if ( dist2 && n ) PCC_CUDA( cudaMemcpyAsync( dist2, ctx->nbrDist, nq * k * sizeof( float ), cudaMemcpyDeviceToHost, ctx->stream ) );
-    PCC_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    streamWait( ctx->stream );
     return PCCB200_OK;
   } );
 }
@@ -104,7 +113,7 @@ int pccb200_kdtree_order( pccb200_ctx* ctx, const int16_t* xyz, size_t n, uint32
     uploadXyz( ctx, xyz, n, ctx->xyz4 );
     kdBuild( ctx->tree, ctx->xyz4, n, ctx->stream );
     if ( n ) PCC_CUDA( cudaMemcpyAsync( vind, ctx->tree.vind, n * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx->stream ) );
-    PCC_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    streamWait( ctx->stream );
     return PCCB200_OK;
   } );
 }
@@ -120,9 +129,9 @@ int pccb200_normals( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int k, int 
     ctx->normals.reserve( 3 * n );
     kdKnn( ctx->tree, ctx->xyz4, n, ctx->tree.vind, k, ctx->nbr, nullptr, ctx->stream );
     computeNormals( ctx->xyz4, ctx->nbr, k, n, ctx->normals, ctx->stream );
-    if ( orientation == 1 ) orientNormals( ctx->orient, ctx->walkArgs, ctx->xyz4, ctx->nbr, k, ctx->tree.vind, n, ctx->normals, ctx->stream );
+    if ( orientation == 1 ) orientNormals( ctx->orient, ctx->own.orientTmp, ctx->walkArgs, ctx->xyz4, ctx->nbr, k, ctx->tree.vind, n, ctx->normals, ctx->stream );
     PCC_CUDA( cudaMemcpyAsync( normals, ctx->normals, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, ctx->stream ) );
-    PCC_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    streamWait( ctx->stream );
     return PCCB200_OK;
   } );
 }
@@ -136,7 +145,7 @@ int pccb200_weight_normal( pccb200_ctx* ctx, const int16_t* xyz, size_t n, int b
     projectedAreas( ctx->xyz4, n, bits, ctx->faces, ctx->faceCounts, ctx->stream );
     unsigned cnt[3];
     PCC_CUDA( cudaMemcpyAsync( cnt, ctx->faceCounts, sizeof( cnt ), cudaMemcpyDeviceToHost, ctx->stream ) );
-    PCC_CUDA( cudaStreamSynchronize( ctx->stream ) );
+    streamWait( ctx->stream );
     // three numbers on the host: order the planes by area (stable, ascending) and derive the weights
     int order[3] = { 0, 1, 2 };
     for ( int a = 1; a < 3; ++a )
@@ -194,7 +203,7 @@ int pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* 
     if ( prm->normal_orientation == 1 ) {
       ProfScope t( pf, "orient", s );
       ctx->orient.prof = pf;
-      orientNormals( ctx->orient, ctx->walkArgs, ctx->xyz4, ctx->nbr, k, ctx->tree.vind, n, ctx->normals, s );
+      orientNormals( ctx->orient, ctx->own.orientTmp, ctx->walkArgs, ctx->xyz4, ctx->nbr, k, ctx->tree.vind, n, ctx->normals, s );
     }
     if ( normals ) PCC_CUDA( cudaMemcpyAsync( normals, ctx->normals, 3 * n * sizeof( double ), cudaMemcpyDeviceToHost, s ) );
     {
@@ -204,13 +213,13 @@ int pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* 
     if ( part0 ) PCC_CUDA( cudaMemcpyAsync( part0, ctx->partition, n, cudaMemcpyDeviceToHost, s ) );
     {
       ProfScope t( pf, "refine", s );
-      refineSegmentation( ctx->refine, ctx->xyz4, ctx->normals, n, *prm, ctx->partition, s );
+      refineSegmentation( ctx->own.refine, ctx->xyz4, ctx->normals, n, *prm, ctx->partition, s );
     }
     if ( part1 ) PCC_CUDA( cudaMemcpyAsync( part1, ctx->partition, n, cudaMemcpyDeviceToHost, s ) );
     PatchResult res;
     {
       ProfScope t( pf, "patches", s );
-      segmentPatches( ctx->patch, res, ctx->xyz4, ctx->rgb4, ctx->nbr, k, ctx->partition, n, *prm, s );
+      segmentPatches( ctx->own.patch, res, ctx->xyz4, ctx->rgb4, ctx->nbr, k, ctx->partition, n, *prm, s );
     }
     {
       ProfScope t( pf, "d2h", s );
@@ -219,7 +228,7 @@ int pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* 
       if ( res.depthElems ) PCC_CUDA( cudaMemcpyAsync( pl->depth.data(), res.depth, res.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, s ) );
       if ( res.occElems ) PCC_CUDA( cudaMemcpyAsync( pl->occ.data(), res.occ, res.occElems, cudaMemcpyDeviceToHost, s ) );
     }
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
     ctx->prof.collect( s );
     *out = pl;
     return PCCB200_OK;

@@ -509,31 +509,31 @@ void blockToPatchFromVideo( const CanvasPatch* dPatches, int numPatches, int max
 
 size_t reconstructPoints( const CanvasPatch* dPatches, const long long* dElemBase, int numPatches, long long totalElems, int occRes, int prec, int W,
                           int H, const uint8_t* om, const uint32_t* blockToPatch, const uint16_t* geo0, const uint16_t* geo1, ReconScratch& rc,
-                          cudaStream_t s ) {
+                          ReconTemp& tmp, cudaStream_t s ) {
   rc.numPoints = 0;
   if ( totalElems == 0 || numPatches == 0 ) return 0;
-  rc.counts.reserve( totalElems + 1 ), rc.offsets.reserve( totalElems + 2 ), rc.scanTmp.reserve( scanTmpElems( totalElems ) );
+  tmp.counts.reserve( totalElems + 1 ), tmp.offsets.reserve( totalElems + 2 ), tmp.scanTmp.reserve( scanTmpElems( totalElems ) );
   kReconstructCount<<<divUp( totalElems, 256 ), 256, 0, s>>>( dPatches, dElemBase, numPatches, totalElems, occRes, prec, W, H, om, blockToPatch, geo0,
-                                                              geo1, rc.counts );
-  exclusiveScanU32( rc.counts, rc.offsets, totalElems, rc.scanTmp, s );
+                                                              geo1, tmp.counts );
+  exclusiveScanU32( tmp.counts, tmp.offsets, totalElems, tmp.scanTmp, s );
   uint32_t R = 0;
-  PCC_CUDA( cudaMemcpyAsync( &R, rc.offsets.p + totalElems, sizeof( uint32_t ), cudaMemcpyDeviceToHost, s ) );
-  PCC_CUDA( cudaStreamSynchronize( s ) );
+  PCC_CUDA( cudaMemcpyAsync( &R, tmp.offsets.p + totalElems, sizeof( uint32_t ), cudaMemcpyDeviceToHost, s ) );
+  streamWait( s );
   rc.numPoints = R;
   if ( R == 0 ) return 0;
   rc.recXyz.reserve( R ), rc.pointToPixel.reserve( 3 * size_t( R ) ), rc.recPartition.reserve( R ), rc.boundary.reserve( R );
   kReconstructEmit<<<divUp( totalElems, 256 ), 256, 0, s>>>( dPatches, dElemBase, numPatches, totalElems, occRes, prec, W, H, om, blockToPatch, geo0,
-                                                             geo1, rc.offsets, rc.recXyz, rc.pointToPixel, rc.recPartition );
+                                                             geo1, tmp.offsets, rc.recXyz, rc.pointToPixel, rc.recPartition );
   kBoundary<<<divUp( R, 256 ), 256, 0, s>>>( rc.pointToPixel, int( R ), om, W, H, prec, rc.boundary );
   PCC_LAUNCH_CHECK();
   return R;
 }
 
-void formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, size_t R, const uint8_t* om, int W, int H, int prec, AttrImages& at,
-                          cudaStream_t s ) {
+void formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, size_t R, const uint8_t* om, int W, int H, int prec, AttrImages& out,
+                          AttrTemp& at, cudaStream_t s ) {
   const size_t Q = size_t( W ) * H;
   at.T[0].reserve( Q ), at.T[1].reserve( Q ), at.tmp.reserve( Q ), at.occ.reserve( Q );
-  for ( int m = 0; m < 2; ++m ) at.rawPlanes[m].reserve( 3 * Q ), at.planes[m].reserve( 3 * Q );
+  for ( int m = 0; m < 2; ++m ) out.rawPlanes[m].reserve( 3 * Q ), out.planes[m].reserve( 3 * Q );
   PCC_CUDA( cudaMemsetAsync( at.T[0], 0, Q * sizeof( ushort4 ), s ) );
   PCC_CUDA( cudaMemsetAsync( at.T[1], 0, Q * sizeof( ushort4 ), s ) );
   if ( R ) {
@@ -541,7 +541,7 @@ void formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, si
     kAttrFallback<<<divUp( R, 256 ), 256, 0, s>>>( pointToPixel, recRgb, int( R ), W, at.T[1] );
   }
   kUpsampleOccupancy<<<divUp( Q, 256 ), 256, 0, s>>>( om, W, H, prec, at.occ );
-  for ( int m = 0; m < 2; ++m ) kToPlanes<<<divUp( Q, 256 ), 256, 0, s>>>( at.T[m], Q, at.rawPlanes[m] );
+  for ( int m = 0; m < 2; ++m ) kToPlanes<<<divUp( Q, 256 ), 256, 0, s>>>( at.T[m], Q, out.rawPlanes[m] );
   // push-pull pyramid (shared by both maps: levels are rebuilt per map)
   std::vector<int> lw, lh;
   {
@@ -577,7 +577,7 @@ void formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, si
       if ( a != dst ) PCC_CUDA( cudaMemcpyAsync( dst, a, n * sizeof( ushort4 ), cudaMemcpyDeviceToDevice, s ) );
       iters = std::min( iters + 1, 16 );
     }
-    kToPlanes<<<divUp( Q, 256 ), 256, 0, s>>>( at.T[m], Q, at.planes[m] );
+    kToPlanes<<<divUp( Q, 256 ), 256, 0, s>>>( at.T[m], Q, out.planes[m] );
   }
   PCC_LAUNCH_CHECK();
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,41 @@ struct CudaError {
 #define PCC_LAUNCH_CHECK() PCC_CUDA( cudaGetLastError() )
 
 static inline int divUp( size_t a, size_t b ) { return int( ( a + b - 1 ) / b ); }
+
+// Host wait for everything queued on `s` so far. BLOCKING (the thread sleeps until the device raises the event) instead of
+// cudaStreamSynchronize's default spin: a GOF keeps one host thread per frame and several GOFs are in flight, far more threads
+// than the host has cores - a spinning waiter would burn the time slice a thread with kernels to launch is waiting for.
+struct BlockingEvent {
+  cudaEvent_t ev  = nullptr;
+  int         dev = -1;
+  ~BlockingEvent() {
+    if ( ev ) cudaEventDestroy( ev );
+  }
+};
+static inline bool spinWaits() {  // PCCB200_SPIN_WAIT=1: the driver's default (lowest latency when threads <= cores)
+  static const bool spin = [] {
+    const char* e = getenv( "PCCB200_SPIN_WAIT" );
+    return e && e[0] == '1';
+  }();
+  return spin;
+}
+static inline void streamWait( cudaStream_t s ) {
+  if ( spinWaits() ) {
+    PCC_CUDA( cudaStreamSynchronize( s ) );
+    return;
+  }
+  thread_local BlockingEvent be;
+  int                        dev = 0;
+  PCC_CUDA( cudaGetDevice( &dev ) );
+  if ( !be.ev || be.dev != dev ) {
+    if ( be.ev ) cudaEventDestroy( be.ev );
+    be.ev = nullptr;
+    PCC_CUDA( cudaEventCreateWithFlags( &be.ev, cudaEventBlockingSync | cudaEventDisableTiming ) );
+    be.dev = dev;
+  }
+  PCC_CUDA( cudaEventRecord( be.ev, s ) );
+  PCC_CUDA( cudaEventSynchronize( be.ev ) );
+}
 
 // Grow-only device buffer; reused across frames so the steady state does no cudaMalloc.
 template <typename T>
@@ -65,7 +101,7 @@ struct DevBuf {
     PCC_CUDA( cudaMalloc( &q, want * sizeof( T ) ) );
     if ( p ) {
       PCC_CUDA( cudaMemcpyAsync( q, p, cap * sizeof( T ), cudaMemcpyDeviceToDevice, s ) );
-      PCC_CUDA( cudaStreamSynchronize( s ) );
+      streamWait( s );
       cudaFree( p );
     }
     p   = q;
@@ -131,7 +167,7 @@ struct Profiler {
   std::vector<bool> closed;
   void              collect( cudaStream_t s ) {
     if ( !enabled ) return;
-    cudaStreamSynchronize( s );
+    streamWait( s );
     for ( size_t i = 0; i < spans.size(); ++i ) {
       float ms = 0, st = -1.f;
       if ( closed[i] ) cudaEventElapsedTime( &ms, spans[i].a, spans[i].b );

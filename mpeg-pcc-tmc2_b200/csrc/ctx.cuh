@@ -1,5 +1,6 @@
 // ctx.cuh — the library context and per-frame state shared by api.cu and gof.cu.
 #pragma once
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -20,8 +21,7 @@ struct FrameState {
   DevBuf<uint32_t> nbr;
   DevBuf<double>   normals;
   OrientScratch    orient;
-  RefineScratch    refine;
-  PatchScratch     patch;
+  FrameScratch*    fat = nullptr;  // leased for the duration of one stage group (ScratchLease)
   PatchResult      seg;  // patches in creation order + device arenas
   // canvas
   std::vector<pccb200_patch> packed;  // packed (sorted) order, u0/v0/orientation filled
@@ -32,7 +32,6 @@ struct FrameState {
   int                        heightPx = 0, maxPatchPixels = 1, maxPatchBlocks = 1;
   CanvasImages               im;
   ReconScratch               rc;
-  ColorScratch               color;
   AttrImages                 attr;
   Profiler                   prof;
   bool                       decodedSet = false;  // the caller replaced om/geo0/geo1 by decoded planes
@@ -60,8 +59,7 @@ struct pccb200_ctx {
   DevBuf<unsigned> faceCounts;
   DevBuf<uchar4>   rgb4;
   OrientScratch    orient;
-  RefineScratch    refine;
-  PatchScratch     patch;
+  FrameScratch     own;  // scratch of the stage-level entry points (the GOF path leases sets from the device pool)
   DevBuf<unsigned char> walkArgs;  // per-frame arguments of a batched orientation walk
   std::vector<std::unique_ptr<FrameState>> framePool;  // reused by successive GOFs (gof.cu)
   ~pccb200_ctx();
@@ -75,6 +73,35 @@ struct pccb200_patchlist {
 
 
 namespace pccb200 {
+
+// Holds one FrameScratch set of the device for a frame while a stage group runs on its stream; the stream is drained before the
+// set goes back to the pool (the next holder may be another frame on another stream).
+struct ScratchLease {
+  FrameState& fs;
+  int         device;
+  const char* holdName;
+  std::chrono::steady_clock::time_point t1;
+  // (with the profiler on, the host-side wait for a set and the wall time it was held are reported as spans without a start)
+  ScratchLease( FrameState& f, int dev, const char* hold = "hold" ) : fs( f ), device( dev ), holdName( hold ) {
+    const auto t0 = std::chrono::steady_clock::now();
+    fs.fat        = acquireFrameScratch( dev );
+    t1            = std::chrono::steady_clock::now();
+    if ( fs.prof.enabled ) fs.prof.results.push_back( Profiler::Result{ "lease_wait", std::chrono::duration<float, std::milli>( t1 - t0 ).count(), -1.f } );
+  }
+  ~ScratchLease() {
+    try {
+      streamWait( fs.stream );
+    } catch ( const CudaError& ) {
+      cudaGetLastError();  // (the failure is reported by the next checked call on this stream)
+    }
+    releaseFrameScratch( device, fs.fat );
+    fs.fat = nullptr;
+    if ( fs.prof.enabled )
+      fs.prof.results.push_back( Profiler::Result{ holdName, std::chrono::duration<float, std::milli>( std::chrono::steady_clock::now() - t1 ).count(), -1.f } );
+  }
+  ScratchLease( const ScratchLease& )            = delete;
+  ScratchLease& operator=( const ScratchLease& ) = delete;
+};
 
 template <class F>
 inline int guarded( pccb200_ctx* ctx, F&& f ) {

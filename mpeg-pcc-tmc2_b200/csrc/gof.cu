@@ -42,7 +42,7 @@ int forEachFrame( pccb200_gof* g, F&& fn ) {
       try {
         PCC_CUDA( cudaSetDevice( g->ctx->device ) );
         fn( fs, f );
-        PCC_CUDA( cudaStreamSynchronize( fs.stream ) );
+        streamWait( fs.stream );
       } catch ( const CudaError& e ) {
         char buf[512];
         snprintf( buf, sizeof( buf ), "frame %d: CUDA error %d (%s) at %s:%d", f, int( e.code ), cudaGetErrorString( e.code ), e.file, e.line );
@@ -130,7 +130,7 @@ void segmentFrameBeforeWalk( FrameState& fs, const pccb200_seg_params& prm ) {
   if ( prm.normal_orientation == 1 ) {
     ProfScope t( pf, "orient", s );
     fs.orient.prof = pf;
-    orientPrepare( fs.orient, fs.xyz4, fs.nbr, k, fs.tree.vind, n, fs.normals, s );
+    orientPrepare( fs.orient, fs.fat->orientTmp, fs.xyz4, fs.nbr, k, fs.tree.vind, n, fs.normals, s );
   }
 }
 
@@ -148,11 +148,11 @@ void segmentFrameAfterWalk( FrameState& fs, const pccb200_seg_params& prm ) {
   }
   {
     ProfScope t( pf, "refine", s );
-    refineSegmentation( fs.refine, fs.xyz4, fs.normals, n, prm, fs.partition, s );
+    refineSegmentation( fs.fat->refine, fs.xyz4, fs.normals, n, prm, fs.partition, s );
   }
   {
     ProfScope t( pf, "patches", s );
-    segmentPatches( fs.patch, fs.seg, fs.xyz4, fs.rgb4, fs.nbr, k, fs.partition, n, prm, s );
+    segmentPatches( fs.fat->patch, fs.seg, fs.xyz4, fs.rgb4, fs.nbr, k, fs.partition, n, prm, s );
   }
 }
 
@@ -200,7 +200,7 @@ void packFrame( FrameState& fs, const pccb200_seg_params& prm, int presetWidth, 
   int res[2] = { 0, 0 };
   PCC_CUDA( cudaMemcpyAsync( cp.data(), fs.dPatches, P * sizeof( CanvasPatch ), cudaMemcpyDeviceToHost, s ) );
   PCC_CUDA( cudaMemcpyAsync( res, fs.packResult, sizeof( res ), cudaMemcpyDeviceToHost, s ) );
-  PCC_CUDA( cudaStreamSynchronize( s ) );
+  streamWait( s );
   if ( res[1] ) throw std::runtime_error( "patch packing exceeded the maximum canvas height" );
   for ( int i = 0; i < P; ++i ) fs.packed[i].u0 = cp[i].u0, fs.packed[i].v0 = cp[i].v0, fs.packed[i].orientation = cp[i].orientation;
   fs.heightPx = res[0];
@@ -209,7 +209,7 @@ void packFrame( FrameState& fs, const pccb200_seg_params& prm, int presetWidth, 
 size_t copyOut( void* dst, const void* dev, size_t elems, size_t elemBytes, cudaStream_t s ) {
   if ( dst && elems ) {
     PCC_CUDA( cudaMemcpyAsync( dst, dev, elems * elemBytes, cudaMemcpyDeviceToHost, s ) );
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
   }
   return elems;
 }
@@ -231,6 +231,7 @@ int runCanvasStages( pccb200_gof* g, int stopAfter ) {
   const bool haveImages = g->stage >= 2;
   rc = forEachFrame( g, [&]( FrameState& fs, int ) {
         cudaStream_t s = fs.stream;
+        ScratchLease lease( fs, g->ctx->device, "hold_canvas" );
         if ( !haveImages ) {
           {
             ProfScope t( &fs.prof, "images", s );
@@ -239,7 +240,7 @@ int runCanvasStages( pccb200_gof* g, int stopAfter ) {
           }
           int err = 0;
           PCC_CUDA( cudaMemcpyAsync( &err, fs.im.error, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
-          PCC_CUDA( cudaStreamSynchronize( s ) );
+          streamWait( s );
           if ( err ) throw std::runtime_error( "patch2Canvas out of the canvas" );
         } else if ( fs.decodedSet ) {
           // decoded occupancy video: a18 again (generateBlockToPatchFromOccupancyMapVideo runs on the decoded frame, :168)
@@ -251,18 +252,18 @@ int runCanvasStages( pccb200_gof* g, int stopAfter ) {
         {
           ProfScope t( &fs.prof, "reconstruct", s );
           reconstructPoints( fs.dPatches, fs.elemBase, int( fs.packed.size() ), fs.totalElems, g->prm.occupancy_resolution, g->occPrec, Wi, Hi, fs.im.om,
-                             fs.im.blockToPatch, fs.im.geo0, fs.im.geo1, fs.rc, s );
+                             fs.im.blockToPatch, fs.im.geo0, fs.im.geo1, fs.rc, fs.fat->recon, s );
         }
         if ( stopAfter == 3 ) return;
         const size_t R = fs.rc.numPoints;
         fs.recRgb.reserve( R + 1 );
         {
           ProfScope t( &fs.prof, "color_transfer", s );
-          transferColors( fs.color, fs.tree, fs.xyz4, fs.rgb4, fs.n, fs.rc.recXyz, R, fs.recRgb, s );
+          transferColors( fs.fat->color, fs.tree, fs.xyz4, fs.rgb4, fs.n, fs.rc.recXyz, R, fs.recRgb, s );
         }
         {
           ProfScope t( &fs.prof, "attribute_images", s );
-          formAttributeImages( fs.rc.pointToPixel, fs.recRgb, R, fs.im.om, Wi, Hi, g->occPrec, fs.attr, s );
+          formAttributeImages( fs.rc.pointToPixel, fs.recRgb, R, fs.im.om, Wi, Hi, g->occPrec, fs.attr, fs.fat->attr, s );
         }
       } );
   if ( rc != PCCB200_OK ) return rc;
@@ -317,14 +318,19 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
     int       rc   = forEachFrame( g, [&]( FrameState& fs, int ) {
       std::exception_ptr early;
       try {
+        ScratchLease lease( fs, ctx->device, "hold_pre" );  // (drains the stream before the set is handed on)
         segmentFrameBeforeWalk( fs, g->prm );
-        PCC_CUDA( cudaStreamSynchronize( fs.stream ) );
+        streamWait( fs.stream );
       } catch ( ... ) {
         early = std::current_exception();  // (this frame still has to show up at the gate, or the others would wait forever)
       }
       gate.arrive( early || fs.orient.walkSmem == 0 ? nullptr : &fs.orient, ctx );
       if ( early ) std::rethrow_exception( early );
-      segmentFrameAfterWalk( fs, g->prm );
+      {
+        ScratchLease lease( fs, ctx->device, "hold_post" );
+        segmentFrameAfterWalk( fs, g->prm );
+        streamWait( fs.stream );
+      }
       packFrame( fs, g->prm, minW, minH, 2, 1.0 );
     } );
     if ( rc != PCCB200_OK ) {
@@ -354,7 +360,7 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
         ProfScope t( &fs.prof, "d2h_patches", fs.stream );
         if ( fs.seg.depthElems ) PCC_CUDA( cudaMemcpyAsync( depth.data(), fs.seg.depth, fs.seg.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, fs.stream ) );
         if ( fs.seg.occElems ) PCC_CUDA( cudaMemcpyAsync( occ.data(), fs.seg.occ, fs.seg.occElems, cudaMemcpyDeviceToHost, fs.stream ) );
-        PCC_CUDA( cudaStreamSynchronize( fs.stream ) );
+        streamWait( fs.stream );
       }
       // the device arenas are in creation order; hand the maps out in packed order (the order of the patch records)
       pl.depth.resize( fs.seg.depthElems ), pl.occ.resize( fs.seg.occElems );
@@ -399,7 +405,7 @@ int pccb200_gof_set_decoded( pccb200_gof* g, int f, const uint8_t* occVideo, con
     if ( occVideo ) PCC_CUDA( cudaMemcpyAsync( fs.im.om, occVideo, cells, cudaMemcpyHostToDevice, fs.stream ) );
     if ( geo0 ) PCC_CUDA( cudaMemcpyAsync( fs.im.geo0, geo0, Q * 2, cudaMemcpyHostToDevice, fs.stream ) );
     if ( geo1 ) PCC_CUDA( cudaMemcpyAsync( fs.im.geo1, geo1, Q * 2, cudaMemcpyHostToDevice, fs.stream ) );
-    PCC_CUDA( cudaStreamSynchronize( fs.stream ) );
+    streamWait( fs.stream );
     fs.decodedSet = fs.decodedSet || occVideo != nullptr;
     return PCCB200_OK;
   } );
@@ -446,7 +452,7 @@ int pccb200_generate_point_cloud( pccb200_ctx* ctx, const pccb200_patch* patches
     PCC_CUDA( cudaMemcpyAsync( fs.im.geo1, geo1, Q * 2, cudaMemcpyHostToDevice, s ) );
     blockToPatchFromVideo( fs.dPatches, P, maxBlocks, occRes, occupancyPrecision, W, H, fs.im.om, fs.im.blockToPatch, s );
     const size_t R = reconstructPoints( fs.dPatches, fs.elemBase, P, total, occRes, occupancyPrecision, W, H, fs.im.om, fs.im.blockToPatch, fs.im.geo0,
-                                        fs.im.geo1, fs.rc, s );
+                                        fs.im.geo1, fs.rc, ctx->own.recon, s );
     *recPoints = R;
     if ( R > capacity ) return ( xyz || pointToPixel || partition || boundary ) ? PCCB200_ERR_CAPACITY : PCCB200_OK;
     if ( R ) {
@@ -459,7 +465,7 @@ int pccb200_generate_point_cloud( pccb200_ctx* ctx, const pccb200_patch* patches
       if ( partition ) PCC_CUDA( cudaMemcpyAsync( partition, fs.rc.recPartition, R * 4, cudaMemcpyDeviceToHost, s ) );
       if ( boundary ) PCC_CUDA( cudaMemcpyAsync( boundary, fs.rc.boundary, R * 2, cudaMemcpyDeviceToHost, s ) );
     }
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
     return PCCB200_OK;
   } );
 }

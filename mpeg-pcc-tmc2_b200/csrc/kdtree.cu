@@ -405,6 +405,7 @@ void kdBuild( KdTree& t, const short4* xyz4, size_t n, cudaStream_t s ) {
   t.slotOf.reserve( n ), t.slotOfNext.reserve( n );
   t.slotI[0].reserve( size_t( F_COUNT ) * maxSlots ), t.slotI[1].reserve( size_t( F_COUNT ) * maxSlots );
   t.counters.reserve( 16 );
+  t.hostInts.reserve( 16 );
   const int TB = 256, gridN = divUp( n, TB );
 
   if ( N <= kLeafMaxSize ) {  // the root is a leaf
@@ -418,7 +419,7 @@ void kdBuild( KdTree& t, const short4* xyz4, size_t n, cudaStream_t s ) {
     PCC_CUDA( cudaMemcpyAsync( t.rootBox, t.counters.p + 8, 6 * sizeof( int ), cudaMemcpyDeviceToHost, s ) );
     kGatherPts<<<gridN, TB, 0, s>>>( t.pts, t.vind, t.ptsT, N );
     PCC_LAUNCH_CHECK();
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
     t.numNodes = 1;
     return;
   }
@@ -464,9 +465,9 @@ void kdBuild( KdTree& t, const short4* xyz4, size_t n, cudaStream_t s ) {
     kDivsAndAssign<<<gridN, TB, 0, s>>>( sv, t.pts, t.vind, slotOf, slotOfNext, N );
     kWriteInternal<<<gridS, 128, 0, s>>>( sv, numSlots, nodeCount, t.nodes );
     PCC_LAUNCH_CHECK();
-    int nextSlots = 0;
-    PCC_CUDA( cudaMemcpyAsync( &nextSlots, t.counters, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    PCC_CUDA( cudaMemcpyAsync( t.hostInts.p, t.counters, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+    streamWait( s );
+    const int nextSlots = t.hostInts.p[0];
     nodeCount += 2 * numSlots;
     numSlots = nextSlots;
     cur ^= 1;

@@ -28,6 +28,7 @@ struct KdTree {
   DevBuf<int>       slotOf, slotOfNext;
   DevBuf<int>       slotI[2];  // per-slot int records, double buffered (see kdtree.cu)
   DevBuf<int>       counters;
+  PinBuf<int>       hostInts;  // page-locked landing zone of the per-level read-back (a pageable copy would spin in the driver)
 };
 
 // xyz4: n points already on the device as short4. Builds nodes/vind/ptsT on stream s (host-synchronising).

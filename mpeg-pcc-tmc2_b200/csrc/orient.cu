@@ -17,8 +17,11 @@
 // Frames of a GOF run this stage concurrently on separate streams (one resident warp each).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "stages.cuh"
@@ -175,8 +178,15 @@ struct Levels {
 // Dependent chain per visited point in the common case: neighbour row -> best[] of the 16 neighbours.
 // One CTA (one warp) per frame of the batch: every frame of a GOF walks inside the SAME launch, so the walks hold one hardware
 // queue instead of one each (a long-running kernel blocks whatever is queued behind it on its connection).
-__global__ void __launch_bounds__( 32, 1 ) kWalk( const WalkArgs* __restrict__ batch ) {
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+  unsigned long long t;
+  asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t ) );
+  return t;
+}
+
+__global__ void __launch_bounds__( 32, 1 ) kWalk( const WalkArgs* __restrict__ batch, unsigned long long* __restrict__ stamps ) {
   const WalkArgs a = batch[blockIdx.x];
+  if ( threadIdx.x == 0 ) stamps[2 * blockIdx.x] = globalTimerNs();
   extern __shared__ __align__( 16 ) uint32_t smemAll[];
   uint2* const    rowBuf = reinterpret_cast<uint2*>( smemAll );  // 16 x 8 bytes: landing zone of the next point's neighbour row
   uint64_t* const pendBuf = reinterpret_cast<uint64_t*>( smemAll + 32 );  // 32 x 16 bytes: re-read leaf words (one pair per lane)
@@ -456,6 +466,7 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( const WalkArgs* __restrict__ b
       grow( seedPos, seedFlip != 0 );
     }
   }
+  if ( lane == 0 ) stamps[2 * blockIdx.x + 1] = globalTimerNs();
 #ifdef PCC_WALK_STATS
   if ( lane == 0 ) printf( "walk n=%d popNew=%u popHot=%u popTree=%u refresh=%u stale=%u spill=%u flush=%u treeClear=%u\n", a.n, stNew, stHot, stTree, stRefresh, stStale, stSpill, stFlush, stTreeClr );
 #endif
@@ -493,24 +504,24 @@ __global__ void kFillU32( uint32_t* p, size_t n, uint32_t v ) {
 
 static_assert( sizeof( WalkArgs ) <= sizeof( OrientScratch::walkArgs ), "OrientScratch::walkArgs too small" );
 
-void orientPrepare( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
-                    cudaStream_t s ) {
+void orientPrepare( OrientScratch& sc, OrientTemp& tmp, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n,
+                    double* normals, cudaStream_t s ) {
   sc.walkSmem = 0;
   if ( n == 0 ) return;
   if ( k > 16 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   const size_t E = n * 16;
   if ( E > size_t( kRankMask ) ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
-  sc.nbrSorted.reserve( E ), sc.relBits.reserve( E ), sc.keysA.reserve( E ), sc.keysB.reserve( E );
-  sc.idsA.reserve( E ), sc.idsB.reserve( E ), sc.rankRel.reserve( E ), sc.rankEnd.reserve( E ), sc.rows.reserve( E ), sc.pos.reserve( n );
-  kEdgeKeys<<<divUp( n, 128 ), 128, 0, s>>>( nbr, normals, int( n ), k, sc.nbrSorted, sc.relBits, sc.keysA, sc.idsA );
+  tmp.nbrSorted.reserve( E ), tmp.relBits.reserve( E ), tmp.keysA.reserve( E ), tmp.keysB.reserve( E );
+  tmp.idsA.reserve( E ), tmp.idsB.reserve( E ), tmp.rankRel.reserve( E ), sc.rankEnd.reserve( E ), sc.rows.reserve( E ), sc.pos.reserve( n );
+  kEdgeKeys<<<divUp( n, 128 ), 128, 0, s>>>( nbr, normals, int( n ), k, tmp.nbrSorted, tmp.relBits, tmp.keysA, tmp.idsA );
   PCC_LAUNCH_CHECK();
   size_t tmpBytes = 0;
-  PCC_CUDA( cub::DeviceRadixSort::SortPairs( nullptr, tmpBytes, sc.keysA.p, sc.keysB.p, sc.idsA.p, sc.idsB.p, E, 0, 62, s ) );
-  sc.cubTmp.reserve( tmpBytes + 16 );
-  PCC_CUDA( cub::DeviceRadixSort::SortPairs( sc.cubTmp.p, tmpBytes, sc.keysA.p, sc.keysB.p, sc.idsA.p, sc.idsB.p, E, 0, 62, s ) );
-  kRanks<<<divUp( E, 256 ), 256, 0, s>>>( sc.idsB, sc.relBits, E, sc.rankRel );
+  PCC_CUDA( cub::DeviceRadixSort::SortPairs( nullptr, tmpBytes, tmp.keysA.p, tmp.keysB.p, tmp.idsA.p, tmp.idsB.p, E, 0, 62, s ) );
+  tmp.cubTmp.reserve( tmpBytes + 16 );
+  PCC_CUDA( cub::DeviceRadixSort::SortPairs( tmp.cubTmp.p, tmpBytes, tmp.keysA.p, tmp.keysB.p, tmp.idsA.p, tmp.idsB.p, E, 0, 62, s ) );
+  kRanks<<<divUp( E, 256 ), 256, 0, s>>>( tmp.idsB, tmp.relBits, E, tmp.rankRel );
   kInvert<<<divUp( n, 256 ), 256, 0, s>>>( vind, int( n ), sc.pos );
-  kBuildRows<<<divUp( E, 256 ), 256, 0, s>>>( vind, sc.pos, sc.nbrSorted, sc.rankRel, int( n ), sc.rows );
+  kBuildRows<<<divUp( E, 256 ), 256, 0, s>>>( vind, sc.pos, tmp.nbrSorted, tmp.rankRel, int( n ), sc.rows );
   PCC_LAUNCH_CHECK();
 
   WalkArgs a;
@@ -548,21 +559,30 @@ void orientWalkBatch( OrientScratch* const* frames, int count, DevBuf<unsigned c
     std::call_once( once, [&]() { err = cudaFuncSetAttribute( kWalk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 ); } );
     PCC_CUDA( err );
   }
-  devArgs.reserve( args.size() * sizeof( WalkArgs ) );
+  // device block: the frames' arguments, then one (start, end) %globaltimer pair per frame
+  const size_t argBytes = ( args.size() * sizeof( WalkArgs ) + 15 ) & ~size_t( 15 );
+  devArgs.reserve( argBytes + args.size() * 16 );
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>( devArgs.p + argBytes );
   PCC_CUDA( cudaMemcpyAsync( devArgs.p, args.data(), args.size() * sizeof( WalkArgs ), cudaMemcpyHostToDevice, s ) );
-  {
-    ProfScope t( prof, "orient_walk", s );
-    kWalk<<<unsigned( args.size() ), 32, smem, s>>>( reinterpret_cast<const WalkArgs*>( devArgs.p ) );
-    PCC_LAUNCH_CHECK();
+  kWalk<<<unsigned( args.size() ), 32, smem, s>>>( reinterpret_cast<const WalkArgs*>( devArgs.p ), stamps );
+  PCC_LAUNCH_CHECK();
+  // The walks run for a second or more on one warp each. NOTHING is enqueued behind them - an event record or a dependent
+  // kernel would sit at the head of the stream's hardware queue until they finish and hold up every other stream that shares
+  // the queue (there are 32 queues and hundreds of frame streams when several GOFs are in flight). The host polls instead.
+  for ( ;; ) {
+    const cudaError_t q = cudaStreamQuery( s );
+    if ( q == cudaSuccess ) break;
+    if ( q != cudaErrorNotReady ) PCC_CUDA( q );
+    std::this_thread::sleep_for( std::chrono::microseconds( 200 ) );
   }
-  // The walks run for a long time on one warp each. The host waits BLOCKING (sleeping): nothing that depends on them is
-  // enqueued before they have finished, and no thread spins on the driver meanwhile.
-  cudaEvent_t done;
-  PCC_CUDA( cudaEventCreateWithFlags( &done, cudaEventBlockingSync | cudaEventDisableTiming ) );
-  cudaError_t err = cudaEventRecord( done, s );
-  if ( err == cudaSuccess ) err = cudaEventSynchronize( done );
-  cudaEventDestroy( done );
-  PCC_CUDA( err );
+  if ( prof && prof->enabled ) {  // the span of the launch, timed on the device by the kernel itself
+    std::vector<unsigned long long> h( 2 * args.size() );
+    PCC_CUDA( cudaMemcpyAsync( h.data(), stamps, h.size() * 8, cudaMemcpyDeviceToHost, s ) );
+    streamWait( s );
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for ( size_t i = 0; i < args.size(); ++i ) t0 = std::min( t0, h[2 * i] ), t1 = std::max( t1, h[2 * i + 1] );
+    prof->results.push_back( Profiler::Result{ "orient_walk", float( double( t1 - t0 ) * 1e-6 ), -1.f } );
+  }
 }
 
 void orientFinish( OrientScratch& sc, const short4* pts, size_t n, double* normals, cudaStream_t s ) {
@@ -572,9 +592,9 @@ void orientFinish( OrientScratch& sc, const short4* pts, size_t n, double* norma
   PCC_LAUNCH_CHECK();
 }
 
-void orientNormals( OrientScratch& sc, DevBuf<unsigned char>& devArgs, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n,
-                    double* normals, cudaStream_t s ) {
-  orientPrepare( sc, pts, nbr, k, vind, n, normals, s );
+void orientNormals( OrientScratch& sc, OrientTemp& tmp, DevBuf<unsigned char>& devArgs, const short4* pts, const uint32_t* nbr, int k,
+                    const uint32_t* vind, size_t n, double* normals, cudaStream_t s ) {
+  orientPrepare( sc, tmp, pts, nbr, k, vind, n, normals, s );
   OrientScratch* one = &sc;
   orientWalkBatch( &one, 1, devArgs, sc.prof, s );
   orientFinish( sc, pts, n, normals, s );

@@ -437,7 +437,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
   kBounds<<<gridN, TB, 0, s>>>( pts, N, sc.ints.p + 2 );
   int mm[6];
   PCC_CUDA( cudaMemcpyAsync( mm, sc.ints.p + 2, sizeof( mm ), cudaMemcpyDeviceToHost, s ) );
-  PCC_CUDA( cudaStreamSynchronize( s ) );
+  streamWait( s );
   Bitmap3 bm;
   for ( int d = 0; d < 3; ++d ) bm.mn[d] = mm[d], bm.dim[d] = mm[3 + d] - mm[d] + 1;
   bm.wordsX             = ( bm.dim[0] + 31 ) / 32;
@@ -457,7 +457,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
       for ( int r = 0; r < 4; ++r ) kPropagate<<<divUp( n, 128 ), 128, 0, s>>>( nbr, sc.raw, partition, sc.parent, N, k, sc.compLabel, sc.ints );
       int changed = 0;
       PCC_CUDA( cudaMemcpyAsync( &changed, sc.ints, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
-      PCC_CUDA( cudaStreamSynchronize( s ) );
+      streamWait( s );
       if ( !changed ) break;
     }
     kLabelAndCount<<<gridN, TB, 0, s>>>( sc.raw, sc.parent, sc.compLabel, N, sc.label, sc.compSize );
@@ -465,7 +465,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
     exclusiveScanU32( sc.kept, sc.keptScan, n, sc.scanTmp, s );
     uint32_t numNew = 0;
     PCC_CUDA( cudaMemcpyAsync( &numNew, sc.keptScan.p + n, sizeof( uint32_t ), cudaMemcpyDeviceToHost, s ) );
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
     if ( numNew == 0 ) break;
     ++out.outerIterations;
     // ---- per-patch extents
@@ -480,7 +480,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
     std::vector<PatchStats> hStats( numNew );
     std::vector<uint8_t>    hView( numNew );
     PCC_CUDA( cudaMemcpyAsync( hStats.data(), dStats, numNew * sizeof( PatchStats ), cudaMemcpyDeviceToHost, s ) );
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
     // view ids: partition[seed] — gather on the host side from a small device read
     sc.seedIdx.reserve( numNew ), sc.seedView.reserve( numNew );
     {
@@ -489,7 +489,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
       PCC_CUDA( cudaMemcpyAsync( sc.seedIdx, seeds.data(), numNew * sizeof( uint32_t ), cudaMemcpyHostToDevice, s ) );
       gatherU8( partition, sc.seedIdx, numNew, sc.seedView, s );
       PCC_CUDA( cudaMemcpyAsync( hView.data(), sc.seedView, numNew, cudaMemcpyDeviceToHost, s ) );
-      PCC_CUDA( cudaStreamSynchronize( s ) );
+      streamWait( s );
     }
     std::vector<DevPatch>  hPatches( numNew );
     std::vector<long long> hDepthOff( numNew ), hOccOff( numNew );
@@ -542,7 +542,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
         std::fill( hPeak.begin() + hPatches[j].blkOff, hPeak.begin() + hPatches[j].blkOff + (long long)hPatches[j].sizeU0 * hPatches[j].sizeV0, v );
       }
       if ( blk ) PCC_CUDA( cudaMemcpyAsync( sc.peak, hPeak.data(), blk * sizeof( int ), cudaMemcpyHostToDevice, s ) );
-      PCC_CUDA( cudaStreamSynchronize( s ) );  // hPeak goes out of scope
+      streamWait( s );  // hPeak goes out of scope
     }
     PCC_CUDA( cudaMemsetAsync( out.occ.p + hOccOff[0], 0, out.occElems - size_t( hOccOff[0] ), s ) );
     kDepth0<<<gridN, TB, 0, s>>>( pts, sc.member, N, dPatches, sc.keys );
@@ -562,7 +562,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
     unsigned                   rawCount = 0;
     PCC_CUDA( cudaMemcpyAsync( hCnt.data(), dCounters, numNew * sizeof( PatchCounters ), cudaMemcpyDeviceToHost, s ) );
     PCC_CUDA( cudaMemcpyAsync( &rawCount, sc.ints.p + 1, sizeof( unsigned ), cudaMemcpyDeviceToHost, s ) );
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
     for ( uint32_t j = 0; j < numNew; ++j ) {
       pccb200_patch& m = out.patches[firstNew + j];
       m.d0_count       = hCnt[j].d0Count;

@@ -424,7 +424,7 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
   kMaxCoord<<<divUp( n, 256 ), 256, 0, s>>>( pts, N, sc.ints );
   int geoMax = 0;
   PCC_CUDA( cudaMemcpyAsync( &geoMax, sc.ints, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
-  PCC_CUDA( cudaStreamSynchronize( s ) );
+  streamWait( s );
   size_t geoRange = 1;
   for ( size_t i = size_t( int16_t( geoMax ) - 1 ); i != 0u; i >>= 1, geoRange <<= 1 ) {}
   int voxShift = 0, gridShift = 0;
@@ -447,7 +447,7 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
   exclusiveScanU32( sc.head, sc.headScan, n, sc.scanTmp, s );
   uint32_t Vu = 0;
   PCC_CUDA( cudaMemcpyAsync( &Vu, sc.headScan.p + n, sizeof( uint32_t ), cudaMemcpyDeviceToHost, s ) );
-  PCC_CUDA( cudaStreamSynchronize( s ) );
+  streamWait( s );
   const int V = int( Vu );
   if ( V >= ( 1 << 24 ) ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   sc.runStart.reserve( V + 1 ), sc.runFirst.reserve( V ), sc.runId.reserve( V ), sc.runFirstSorted.reserve( V ), sc.order.reserve( V );
@@ -464,7 +464,7 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
   kCenterBounds<<<divUp( V, 256 ), 256, 0, s>>>( sc.centers, V, sc.ints.p + 2 );
   int mm[6];
   PCC_CUDA( cudaMemcpyAsync( mm, sc.ints.p + 2, sizeof( mm ), cudaMemcpyDeviceToHost, s ) );
-  PCC_CUDA( cudaStreamSynchronize( s ) );
+  streamWait( s );
   GridGeom g;
   g.voxShift = voxShift, g.gridShift = gridShift, g.half = half;
   size_t cells = 1;
@@ -479,7 +479,7 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
     if ( off.size() > size_t( kMaxHits ) ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
     sc.offsets.reserve( off.size() );
     PCC_CUDA( cudaMemcpyAsync( sc.offsets, off.data(), off.size() * sizeof( int ), cudaMemcpyHostToDevice, s ) );
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
     sc.offsetsR2 = r2, sc.numOffsets = int( off.size() );
   }
   sc.adjOff.reserve( V ), sc.adjLen.reserve( V ), sc.nearData.reserve( size_t( V ) * kMaxNear ), sc.nearLen.reserve( V ), sc.weight.reserve( V );
@@ -496,7 +496,7 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
     PCC_LAUNCH_CHECK();
     unsigned long long res[2];
     PCC_CUDA( cudaMemcpyAsync( res, sc.cursor, sizeof( res ), cudaMemcpyDeviceToHost, s ) );
-    PCC_CUDA( cudaStreamSynchronize( s ) );
+    streamWait( s );
     if ( !( res[1] & 0xffffffffull ) ) break;
     capacity = size_t( res[0] ) + size_t( V );  // cursor counted every request, so this is the exact need
   }

@@ -10,11 +10,18 @@ void computeNormals( const short4* pts, const uint32_t* nbr, int k, size_t n, do
 void initialSegmentation( const double* normals, size_t n, const double w[3], uint8_t* partition, cudaStream_t s );
 
 // orient.cu
+// (temporaries of orientPrepare: dead once the rows are built - part of the leased FrameScratch below)
+struct OrientTemp {
+  DevBuf<uint32_t> nbrSorted, relBits, idsA, idsB, rankRel;
+  DevBuf<uint64_t> keysA, keysB;
+  DevBuf<uint8_t>  cubTmp;
+};
+// (what the walk itself and orientFinish read: stays with the frame)
 struct OrientScratch {
-  DevBuf<uint32_t> nbrSorted, relBits, idsA, idsB, rankRel, best, pos, rankEnd;
+  DevBuf<uint32_t> best, pos, rankEnd;
   DevBuf<uint2>    rows;
-  DevBuf<uint64_t> keysA, keysB, L0;
-  DevBuf<uint8_t>  flip, cubTmp;
+  DevBuf<uint64_t> L0;
+  DevBuf<uint8_t>  flip;
   DevBuf<unsigned> counter;
   Profiler*        prof = nullptr;
   alignas( 8 ) unsigned char walkArgs[160];  // the frame's walk arguments, filled by orientPrepare (opaque here)
@@ -22,12 +29,12 @@ struct OrientScratch {
 };
 // Three steps, so that the walks of all frames of a GOF can share one launch: data-parallel preparation on the frame's stream,
 // the walks of a batch of prepared frames (blocks the calling host thread until they are done), sign application.
-void orientPrepare( OrientScratch& sc, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
+void orientPrepare( OrientScratch& sc, OrientTemp& tmp, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n, double* normals,
                     cudaStream_t s );
 void orientWalkBatch( OrientScratch* const* frames, int count, DevBuf<unsigned char>& devArgs, Profiler* prof, cudaStream_t s );
 void orientFinish( OrientScratch& sc, const short4* pts, size_t n, double* normals, cudaStream_t s );
 // all three for one frame
-void orientNormals( OrientScratch& sc, DevBuf<unsigned char>& devArgs, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n,
+void orientNormals( OrientScratch& sc, OrientTemp& tmp, DevBuf<unsigned char>& devArgs, const short4* pts, const uint32_t* nbr, int k, const uint32_t* vind, size_t n,
                     double* normals, cudaStream_t s );
 
 // refine.cu
@@ -79,18 +86,23 @@ struct CanvasImages {
   DevBuf<uint32_t> blockToPatch;
   DevBuf<int>      error;
 };
-struct ReconScratch {
-  DevBuf<uint32_t> counts, offsets, scanTmp, pointToPixel, recPartition;
+struct ReconTemp {
+  DevBuf<uint32_t> counts, offsets, scanTmp;
+};
+struct ReconScratch {  // the reconstructed cloud (a product: stays with the frame)
+  DevBuf<uint32_t> pointToPixel, recPartition;
   DevBuf<short4>   recXyz;
   DevBuf<uint16_t> boundary;
   size_t           numPoints = 0;
 };
-struct AttrImages {
+struct AttrTemp {
   DevBuf<ushort4>               T[2], tmp;
   DevBuf<uint8_t>               occ;
-  DevBuf<uint16_t>              rawPlanes[2], planes[2];
   std::vector<DevBuf<ushort4>>  mip;
   std::vector<DevBuf<uint8_t>>  mipOcc;
+};
+struct AttrImages {  // products: attribute frames before / after padding
+  DevBuf<uint16_t> rawPlanes[2], planes[2];
 };
 int    packPatches( CanvasPatch* dPatches, int numPatches, const uint8_t* occArena, int sizeU, int sizeV, int occRes, int* dResult, cudaStream_t s );
 void   formOccupancyAndGeometry( const CanvasPatch* dPatches, int numPatches, int maxPatchPixels, int maxPatchBlocks, const int16_t* depthArena,
@@ -99,9 +111,9 @@ void   blockToPatchFromVideo( const CanvasPatch* dPatches, int numPatches, int m
                               uint32_t* blockToPatch, cudaStream_t s );
 size_t reconstructPoints( const CanvasPatch* dPatches, const long long* dElemBase, int numPatches, long long totalElems, int occRes, int prec, int W,
                           int H, const uint8_t* om, const uint32_t* blockToPatch, const uint16_t* geo0, const uint16_t* geo1, ReconScratch& rc,
-                          cudaStream_t s );
+                          ReconTemp& tmp, cudaStream_t s );
 void   formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, size_t R, const uint8_t* om, int W, int H, int prec, AttrImages& at,
-                            cudaStream_t s );
+                            AttrTemp& tmp, cudaStream_t s );
 
 // color.cu
 struct ColorScratch {
@@ -113,6 +125,22 @@ struct ColorScratch {
 };
 void transferColors( ColorScratch& sc, const KdTree& srcTree, const short4* srcPts, const uchar4* srcRgb, size_t n, const short4* recPts, size_t R,
                      uchar4* recRgb, cudaStream_t s );
+
+// Everything a frame needs only INSIDE one group of stages (before the orientation walk: sort buffers of the edge keys; after
+// it: refinement grid, patch bitmaps, colour-transfer tree and vote buffers, push-pull pyramid ...): ~1.2 GB at 0.83 Mpts, five
+// times what a frame has to keep while its walk runs. Frames lease one set from a per-device pool for the duration of a stage
+// group (scratch.cu), so the number of frames in flight is bounded by what they KEEP, not by their peak.
+struct FrameScratch {
+  OrientTemp    orientTmp;
+  RefineScratch refine;
+  PatchScratch  patch;
+  ColorScratch  color;
+  ReconTemp     recon;
+  AttrTemp      attr;
+};
+FrameScratch* acquireFrameScratch( int device );             // blocks while all sets of the device are leased
+void          releaseFrameScratch( int device, FrameScratch* );
+int           setFrameScratchSets( int device, int count );  // upper bound of sets (>= 1); returns the previous bound
 
 // util.cu
 void projectedAreas( const short4* pts, size_t n, int bits, uint32_t* faces, unsigned* counts, cudaStream_t s );

@@ -621,6 +621,9 @@ class ProductGof:
     def resume(self, width, height, stop_after=0):
         self.p._check(self.p.lib.pccb200_gof_resume(self.h, width, height, stop_after))
 
+    def count(self, f, what):
+        return self.p.lib.pccb200_gof_get(self.h, f, what, None)
+
     def fetch(self, f, what, out=None):
         cnt = self.p.lib.pccb200_gof_get(self.h, f, what, None)
         if out is None or out.size != cnt:
