@@ -53,7 +53,10 @@ typedef struct pccb200_seg_params {
   int32_t geometry_bitdepth_2d;            /* 8   */
   int32_t geometry_bitdepth_3d;            /* 11 = geometry3dCoordinatesBitdepth+1 */
   int32_t map_count_minus1;                /* 1   */
-  int32_t reserved0;
+  int32_t global_patch_allocation;         /* 0 = all-intra packing (constrainedPack 0, globalPatchAllocation 0: every frame packed on its
+                                              own, PCCEncoder::packFlexible); 1 = random-access packing (cfg/condition/ctc-random-access.cfg:
+                                              constrainedPack 1 + globalPatchAllocation 1: spatialConsistencyPackFlexible against the previous
+                                              frame, then PCCEncoder::performDataAdaptiveGPAMethod over the GOF)                              */
   double  lambda_refine;                   /* 3.0 */
   double  max_allowed_dist2_raw_detection; /* 9.0 */
   double  max_allowed_dist2_raw_selection; /* 1.0 */
@@ -73,6 +76,9 @@ typedef struct pccb200_patch {
   int32_t size_2d_x, size_2d_y; /* patchSize2D{X,Y}InPixel (quantised) */
   int32_t u0, v0, orientation;  /* filled by packing; -1 before */
   int32_t d0_count, eom_and_d1_count;
+  int32_t best_match_idx; /* PCCPatch::bestMatchIdx_: index of the matched patch in the previous frame's list, -1 = none (always -1
+                             in all-intra packing)                                                                             */
+  int32_t is_global;      /* PCCPatch::isGlobalPatch_ (set by the global patch allocation)                                    */
   int64_t depth_offset;   /* into the int16 depth arena: depth_[0] then depth_[1], size_u*size_v each */
   int64_t occ_offset;     /* into the uint8 occupancy arena: size_u0*size_v0 */
 } pccb200_patch;

@@ -29,7 +29,7 @@ struct FrameState {
   DevBuf<long long>          elemBase;
   DevBuf<int>                packResult;
   long long                  totalElems = 0;
-  int                        heightPx = 0, maxPatchPixels = 1, maxPatchBlocks = 1;
+  int                        heightPx = 0, widthPx = 0, maxPatchPixels = 1, maxPatchBlocks = 1;
   CanvasImages               im;
   ReconScratch               rc;
   AttrImages                 attr;
@@ -61,6 +61,7 @@ struct pccb200_ctx {
   OrientScratch    orient;
   FrameScratch     own;  // scratch of the stage-level entry points (the GOF path leases sets from the device pool)
   DevBuf<unsigned char> walkArgs;  // per-frame arguments of a batched orientation walk
+  RaPackScratch         raPack;    // batches of the random-access packer
   std::vector<std::unique_ptr<FrameState>> framePool;  // reused by successive GOFs (gof.cu)
   ~pccb200_ctx();
 };

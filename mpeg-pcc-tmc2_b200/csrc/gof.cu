@@ -168,7 +168,7 @@ void packFrame( FrameState& fs, const pccb200_seg_params& prm, int presetWidth, 
   cudaStream_t s = fs.stream;
   ProfScope    t( &fs.prof, "pack", s );
   fs.packed   = fs.seg.patches;
-  fs.heightPx = presetHeight;
+  fs.heightPx = presetHeight, fs.widthPx = presetWidth;
   const int P = int( fs.packed.size() );
   fs.totalElems = 0, fs.maxPatchPixels = 1, fs.maxPatchBlocks = 1;
   if ( P == 0 ) return;
@@ -204,6 +204,75 @@ void packFrame( FrameState& fs, const pccb200_seg_params& prm, int presetWidth, 
   if ( res[1] ) throw std::runtime_error( "patch packing exceeded the maximum canvas height" );
   for ( int i = 0; i < P; ++i ) fs.packed[i].u0 = cp[i].u0, fs.packed[i].v0 = cp[i].v0, fs.packed[i].orientation = cp[i].orientation;
   fs.heightPx = res[0];
+}
+
+// device-side records of a finished packing (fs.packed with u0 / v0 / orientation set): what a16..a22 read
+void installPacking( FrameState& fs, int occRes ) {
+  cudaStream_t s = fs.stream;
+  const int    P = int( fs.packed.size() );
+  fs.totalElems = 0, fs.maxPatchPixels = 1, fs.maxPatchBlocks = 1;
+  if ( P == 0 ) return;
+  std::vector<CanvasPatch> cp( P );
+  std::vector<long long>   base( P + 1 );
+  for ( int i = 0; i < P; ++i ) {
+    const pccb200_patch& m = fs.packed[i];
+    CanvasPatch&         c = cp[i];
+    c.viewId = m.view_id, c.u1 = m.u1, c.v1 = m.v1, c.d1 = m.d1, c.sizeU = m.size_u, c.sizeV = m.size_v;
+    c.sizeU0 = m.size_u0, c.sizeV0 = m.size_v0, c.u0 = m.u0, c.v0 = m.v0, c.orientation = m.orientation, c.pad = 0;
+    c.depthOff = m.depth_offset, c.occOff = m.occ_offset;
+    base[i]    = fs.totalElems;
+    fs.totalElems += (long long)m.size_u0 * m.size_v0 * occRes * occRes;
+    fs.maxPatchPixels = std::max( fs.maxPatchPixels, m.size_u * m.size_v );
+    fs.maxPatchBlocks = std::max( fs.maxPatchBlocks, m.size_u0 * m.size_v0 );
+  }
+  base[P] = fs.totalElems;
+  fs.dPatches.reserve( P ), fs.elemBase.reserve( P + 1 );
+  PCC_CUDA( cudaMemcpyAsync( fs.dPatches, cp.data(), P * sizeof( CanvasPatch ), cudaMemcpyHostToDevice, s ) );
+  PCC_CUDA( cudaMemcpyAsync( fs.elemBase, base.data(), ( P + 1 ) * sizeof( long long ), cudaMemcpyHostToDevice, s ) );
+  streamWait( s );  // (cp / base are locals)
+}
+
+// a15: random-access packing of the whole GOF (constrainedPack + global patch allocation): every frame is placed against the
+// previous one, so this runs once per GOF after all frames are segmented - metadata on the host, placement searches on the device
+void packGofRa( pccb200_gof* g, int minW, int minH ) {
+  const int               occRes = g->prm.occupancy_resolution;
+  std::vector<ra::Frame>  frames( g->nframes );
+  for ( int f = 0; f < g->nframes; ++f ) {
+    FrameState&          fs = *g->frames[f];
+    std::vector<uint8_t> occ( fs.seg.occElems );
+    if ( fs.seg.occElems ) {
+      PCC_CUDA( cudaMemcpyAsync( occ.data(), fs.seg.occ, fs.seg.occElems, cudaMemcpyDeviceToHost, fs.stream ) );
+      streamWait( fs.stream );
+    }
+    frames[f].patches.resize( fs.seg.patches.size() );
+    for ( size_t i = 0; i < fs.seg.patches.size(); ++i ) {
+      ra::Patch& p = frames[f].patches[i];
+      p.m          = fs.seg.patches[i];
+      p.m.best_match_idx = -1, p.m.is_global = 0;
+      p.occ.assign( occ.begin() + p.m.occ_offset, occ.begin() + p.m.occ_offset + size_t( p.m.size_u0 ) * p.m.size_v0 );
+    }
+  }
+  if ( !packGofRandomAccess( frames, occRes, size_t( minW ), size_t( minH ), g->ctx->raPack, &g->ctx->prof, g->ctx->stream ) )
+    throw std::runtime_error( "random-access packing exceeded the packer's canvas limits" );
+  for ( int f = 0; f < g->nframes; ++f ) {
+    FrameState& fs = *g->frames[f];
+    fs.packed.clear();
+    std::vector<uint8_t> arena;
+    for ( auto& p : frames[f].patches ) {
+      p.m.occ_offset = int64_t( arena.size() );
+      arena.insert( arena.end(), p.occ.begin(), p.occ.end() );
+      fs.packed.push_back( p.m );
+    }
+    fs.seg.occ.reserve( arena.size() + 1 );
+    fs.seg.occElems = arena.size();
+    if ( !arena.empty() ) {
+      PCC_CUDA( cudaMemcpyAsync( fs.seg.occ, arena.data(), arena.size(), cudaMemcpyHostToDevice, fs.stream ) );
+      streamWait( fs.stream );
+    }
+    fs.heightPx = int( frames[f].height );
+    fs.widthPx  = int( frames[f].width );
+    installPacking( fs, occRes );
+  }
 }
 
 size_t copyOut( void* dst, const void* dev, size_t elems, size_t elemBytes, cudaStream_t s ) {
@@ -289,7 +358,7 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
   if ( !ctx || !out || nframes < 0 || ( nframes > 0 && ( !xyz || !rgb || !n ) ) || !prm ) return PCCB200_ERR_BAD_ARG;
   if ( prm->nn_normal_estimation != 16 || prm->max_nn_count_patch_seg != 16 || prm->geometry_bitdepth_3d > 12 || prm->occupancy_resolution != 16 ||
        ( prm->normal_orientation != 0 && prm->normal_orientation != 1 ) || occupancyPrecision < 1 || 16 % occupancyPrecision != 0 ||
-       prm->map_count_minus1 != 1 )
+       prm->map_count_minus1 != 1 || ( prm->global_patch_allocation != 0 && prm->global_patch_allocation != 1 ) )
     return PCCB200_ERR_UNSUPPORTED;
   *out = nullptr;
   return guarded( ctx, [&]() -> int {
@@ -331,15 +400,29 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
         segmentFrameAfterWalk( fs, g->prm );
         streamWait( fs.stream );
       }
-      packFrame( fs, g->prm, minW, minH, 2, 1.0 );
+      if ( g->prm.global_patch_allocation == 0 ) packFrame( fs, g->prm, minW, minH, 2, 1.0 );
     } );
+    if ( rc == PCCB200_OK && g->prm.global_patch_allocation != 0 ) {
+      try {
+        packGofRa( g, minW, minH );
+      } catch ( const std::exception& e ) {
+        ctx->lastError = e.what();
+        rc             = PCCB200_ERR_CUDA;
+      } catch ( const CudaError& e ) {
+        char buf[256];
+        snprintf( buf, sizeof( buf ), "random-access packing: CUDA error %d (%s) at %s:%d", int( e.code ), cudaGetErrorString( e.code ), e.file, e.line );
+        ctx->lastError = buf;
+        rc             = PCCB200_ERR_CUDA;
+        cudaGetLastError();
+      }
+    }
     if ( rc != PCCB200_OK ) {
       delete g;
       return rc;
     }
     // a14: one canvas size per GOF (PCCEncoder::resizeTileGeometryVideo + resizeGeometryVideo, PCCEncoder.cpp:5546-5634)
     size_t W = minW, H = minH;
-    for ( auto* fs : g->frames ) H = std::max( H, size_t( fs->heightPx ) );
+    for ( auto* fs : g->frames ) H = std::max( H, size_t( fs->heightPx ) ), W = std::max( W, size_t( fs->widthPx ) );
     g->W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), g->H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
     g->stage = 1;
     if ( stopAfter != 1 ) {

@@ -498,6 +498,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
     for ( uint32_t j = 0; j < numNew; ++j ) {
       const PatchStats& st = hStats[j];
       pccb200_patch     m{};
+      m.best_match_idx = -1;
       m.index   = int32_t( out.patches.size() );
       m.view_id = hView[j];
       m.normal_axis = hViewAxes[m.view_id][0], m.tangent_axis = hViewAxes[m.view_id][1];

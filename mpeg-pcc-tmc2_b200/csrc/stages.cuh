@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "kdtree.cuh"
+#include "ra_pack.hpp"
 
 namespace pccb200 {
 
@@ -114,6 +115,15 @@ size_t reconstructPoints( const CanvasPatch* dPatches, const long long* dElemBas
                           ReconTemp& tmp, cudaStream_t s );
 void   formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, size_t R, const uint8_t* om, int W, int H, int prec, AttrImages& at,
                             AttrTemp& tmp, cudaStream_t s );
+
+// pack_ra.cu: a15, random-access packing of a whole GOF (host logic in ra_pack.hpp, placement searches on the device)
+struct RaPackScratch {
+  DevBuf<ra::PlaceItem> items;
+  DevBuf<ra::PlaceJob>  jobs;
+  DevBuf<uint8_t>       occ;
+};
+bool packGofRandomAccess( std::vector<ra::Frame>& frames, int occRes, size_t minWidth, size_t minHeight, RaPackScratch& sc, Profiler* prof,
+                          cudaStream_t s );
 
 // color.cu
 struct ColorScratch {

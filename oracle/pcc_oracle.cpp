@@ -6,6 +6,7 @@
 #include "pcc_oracle.h"
 
 #include <algorithm>
+#include <map>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -632,10 +633,18 @@ void pcco_refine_segmentation( const int16_t* xyz, const double* normals, size_t
 //         6 projection planes, no partitioning/expansion/gradient separation), resampling (:362-470).
 // ======================================================================================================
 namespace {
+// GPAPatchData (L/PccLibCommon/include/PCCPatch.h:42-71): a trial placement of the global patch allocation
+struct OGpa {
+  bool                 matched = false, global = false;
+  int                  track = -1, sizeU0 = 0, sizeV0 = 0, u0 = -1, v0 = -1, orient = -1;
+  std::vector<uint8_t> occ;
+  void                 reset() { *this = OGpa(); }
+};
 struct OPatch {
   pccb200_patch        m;
   std::vector<int16_t> depth[2];
   std::vector<uint8_t> occ;
+  OGpa                 cur, pre;  // random-access packing only
 };
 struct OPatchList {
   std::vector<OPatch> patches;
@@ -688,6 +697,7 @@ void* pcco_segment_patches( const int16_t* xyz, const uint8_t* rgb, size_t n, co
       m.normal_axis = kViewAxes[m.view_id][0], m.tangent_axis = kViewAxes[m.view_id][1];
       m.bitangent_axis = kViewAxes[m.view_id][2], m.projection_mode = kViewAxes[m.view_id][3];
       m.u0 = m.v0 = m.orientation = 0;  // PCCPatch defaults before packing
+      m.best_match_idx = -1;
       const int na = m.normal_axis, ta = m.tangent_axis, ba = m.bitangent_axis, mode = m.projection_mode;
       const int dir = 1 - 2 * mode;
       auto      C   = [&]( uint32_t i, int axis ) { return int( xyz[3 * size_t( i ) + axis] ); };
@@ -932,6 +942,443 @@ void packFrame( OFrame& F, int occRes, int presetWidth, int numTilesHor, double 
   F.height = height;
 }
 
+// =====================================================================================================================
+// a15: random-access packing (constrainedPack 1, globalPatchAllocation 1; packingStrategy 1, two orientations, safeguard 0,
+// lowDelayEncoding off, one tile, no raw / EOM patches)
+// =====================================================================================================================
+// canvas of occupancy blocks with the reference's fit / mark rules (PCCPatch::checkFitPatchCanvas, PCCPatch.cpp:310-335; ...ForGPA :667-692)
+struct BlockCanvas {
+  int                  sizeU = 0, sizeV = 0;
+  std::vector<uint8_t> c;
+  BlockCanvas( int u, int v ) : sizeU( u ), sizeV( v ), c( size_t( u ) * v, 0 ) {}
+  static void at( int u0, int v0, int orient, int ub, int vb, int& x, int& y ) {
+    if ( orient == OR_DEFAULT ) x = ub + u0, y = vb + v0;
+    else x = vb + u0, y = ub + v0;
+  }
+  bool fits( int u0, int v0, int orient, int sU0, int sV0 ) const {  // the whole bounding box must be on the canvas and free
+    for ( int vb = 0; vb < sV0; ++vb )
+      for ( int ub = 0; ub < sU0; ++ub ) {
+        int x, y;
+        at( u0, v0, orient, ub, vb, x, y );
+        if ( x >= sizeU || y >= sizeV || c[size_t( y ) * sizeU + x] ) return false;
+      }
+    return true;
+  }
+  void mark( int u0, int v0, int orient, int sU0, int sV0, const std::vector<uint8_t>& occ, int occStride ) {  // occupied blocks only
+    for ( int vb = 0; vb < sV0; ++vb )
+      for ( int ub = 0; ub < sU0; ++ub ) {
+        int x, y;
+        at( u0, v0, orient, ub, vb, x, y );
+        c[size_t( y ) * sizeU + x] |= occ[size_t( vb ) * occStride + ub];
+      }
+  }
+  void grow() {
+    sizeV *= 2;
+    c.resize( size_t( sizeU ) * sizeV, 0 );
+  }
+};
+enum PlaceMode { PLACE_BEST_EFFORT, PLACE_MATCHED, PLACE_KNOWN_ORIENTATION, PLACE_STICKY };
+// One placement. BEST_EFFORT: raster scan, two orientations per position, the order chosen by the aspect of (aspU0, aspV0)
+// (g_orientationHorizontal / g_orientationVertical, PCCCommon.h:131-150). MATCHED: the given position first, then a raster scan
+// with the given orientation (its inclusive loop bounds only add positions that can never fit). KNOWN_ORIENTATION: raster scan
+// with the given orientation. STICKY (a union patch without a reference orientation while a reference frame is in use,
+// PCCEncoder.cpp:7171-7193): the first position tries both orientations; if neither fits, the orientation tried last has
+// overwritten the "unknown" marker, so every later position is tried with that one only. The canvas doubles its height until
+// the patch fits.
+void placeOne( BlockCanvas& cv, int sU0, int sV0, int aspU0, int aspV0, PlaceMode mode, int& u0, int& v0, int& orient ) {
+  for ( ;; ) {
+    if ( mode == PLACE_MATCHED && cv.fits( u0, v0, orient, sU0, sV0 ) ) return;
+    for ( int v = 0; v < cv.sizeV; ++v )
+      for ( int u = 0; u < cv.sizeU; ++u ) {
+        if ( mode == PLACE_BEST_EFFORT || ( mode == PLACE_STICKY && orient == -1 ) ) {
+          for ( int o = 0; o < 2; ++o ) {
+            const int tryO = aspU0 > aspV0 ? ( o == 0 ? OR_SWAP : OR_DEFAULT ) : ( o == 0 ? OR_DEFAULT : OR_SWAP );
+            if ( cv.fits( u, v, tryO, sU0, sV0 ) ) {
+              u0 = u, v0 = v, orient = tryO;
+              return;
+            }
+            if ( mode == PLACE_STICKY ) orient = tryO;
+          }
+        } else if ( cv.fits( u, v, orient, sU0, sV0 ) ) {
+          u0 = u, v0 = v;
+          return;
+        }
+      }
+    cv.grow();
+  }
+}
+inline bool switched( int orient ) { return orient != OR_DEFAULT; }  // isPatchDimensionSwitched for DEFAULT / SWAP
+inline void extend( int u0, int v0, int orient, int sU0, int sV0, int occRes, size_t& width, size_t& height ) {
+  height = std::max( height, size_t( v0 + ( switched( orient ) ? sU0 : sV0 ) ) * occRes );
+  width  = std::max( width, size_t( u0 + ( switched( orient ) ? sV0 : sU0 ) ) * occRes );
+}
+// pcc::computeIOU on the 3-D bounding rectangles (u1, v1, sizeU, sizeV) (PCCPatchSegmenter.cpp:1563-1570, Rect :393-425)
+float rectIou( const pccb200_patch& a, const pccb200_patch& b ) {
+  const int x1 = std::max( a.u1, b.u1 ), y1 = std::max( a.v1, b.v1 );
+  int       w = std::min( a.u1 + a.size_u, b.u1 + b.size_u ) - x1, h = std::min( a.v1 + a.size_v, b.v1 + b.size_v ) - y1;
+  if ( w <= 0 || h <= 0 ) w = h = 0;
+  const int inter = w * h, uni = a.size_u * a.size_v + b.size_u * b.size_v - inter;
+  return static_cast<float>( inter ) / uni;
+}
+
+// PCCEncoder::spatialConsistencyPackFlexible (PCCEncoder.cpp:1183-1412)
+void packFrameAfter( OFrame& F, const OFrame& prev, int occRes, int presetWidth, int numTilesHor, double tileRatio ) {
+  auto& P = F.pl.patches;
+  F.width = presetWidth;
+  if ( P.empty() ) return;
+  std::sort( P.begin(), P.end(), patchBefore );
+  int sizeU = presetWidth / occRes, sizeV = std::max( P[0].m.size_u0, P[0].m.size_v0 );
+  // every patch of the previous frame, in its order, takes the unmatched patch of the same view with the largest IoU (> 0.2)
+  std::vector<OPatch> order;
+  for ( size_t pi = 0; pi < prev.pl.patches.size(); ++pi ) {
+    const pccb200_patch& q = prev.pl.patches[pi].m;
+    float                best = 0.0F;
+    int                  bestIdx = -1;
+    for ( size_t ci = 0; ci < P.size(); ++ci )
+      if ( P[ci].m.view_id == q.view_id && P[ci].m.best_match_idx == -1 ) {
+        const float iou = rectIou( q, P[ci].m );
+        if ( iou > best ) best = iou, bestIdx = int( ci );
+      }
+    if ( best > 0.2F ) {
+      P[bestIdx].m.best_match_idx = int( pi );
+      order.push_back( P[bestIdx] );
+    }
+  }
+  for ( auto& p : P )
+    if ( p.m.best_match_idx == -1 ) order.push_back( p );
+  P = std::move( order );
+  for ( auto& p : P ) sizeU = std::max( sizeU, p.m.size_u0 + 1 );
+  const int tileW = sizeU / numTilesHor, tileH = int( tileW * tileRatio );
+  sizeV           = sizeV >= tileH ? sizeV : tileH;
+  size_t      width = size_t( sizeU ) * occRes, height = size_t( sizeV ) * occRes;
+  BlockCanvas cv( sizeU, sizeV );
+  for ( auto& p : P ) {
+    pccb200_patch& m = p.m;
+    if ( m.best_match_idx != -1 ) {
+      const pccb200_patch& q = prev.pl.patches[m.best_match_idx].m;
+      m.u0 = q.u0, m.v0 = q.v0, m.orientation = q.orientation;
+      placeOne( cv, m.size_u0, m.size_v0, m.size_u0, m.size_v0, PLACE_MATCHED, m.u0, m.v0, m.orientation );
+    } else {
+      placeOne( cv, m.size_u0, m.size_v0, m.size_u0, m.size_v0, PLACE_BEST_EFFORT, m.u0, m.v0, m.orientation );
+    }
+    cv.mark( m.u0, m.v0, m.orientation, m.size_u0, m.size_v0, p.occ, m.size_u0 );
+    extend( m.u0, m.v0, m.orientation, m.size_u0, m.size_v0, occRes, width, height );
+  }
+  F.width = width, F.height = height;
+}
+
+// ---- PCCEncoder::performDataAdaptiveGPAMethod and helpers (PCCEncoder.cpp:6821-7860)
+struct GpaState {
+  std::vector<OFrame>* frames;
+  int                  occRes;
+  size_t               frameWidthIn, frameHeightIn;  // minimumImageWidth / Height
+  std::vector<size_t>  curW, curH, preW, preH;       // Cur / PrePCCGPAFrameSize per frame
+};
+typedef std::map<size_t, std::vector<std::pair<size_t, size_t>>> Tracks;  // GlobalPatches: track -> (frame, patch)
+struct UnionPatch {
+  int                  sizeU0 = 0, sizeV0 = 0, u0 = 0, v0 = 0, orient = 0;
+  std::vector<uint8_t> occ;
+};
+typedef std::map<size_t, UnionPatch> Unions;
+
+// packingFirstFrame (:7226-7356): the first frame of a sub-context is packed on its own (against frame-1 when there is one)
+void gpaPackFirstFrame( GpaState& S, size_t f, bool hasRef ) {
+  OFrame& F = ( *S.frames )[f];
+  auto&   P = F.pl.patches;
+  int     sizeU = int( F.width ) / S.occRes, sizeV = 0;
+  for ( auto& p : P ) sizeV = std::max( sizeV, std::max( p.m.size_u0, p.m.size_v0 ) );
+  for ( auto& p : P ) sizeU = std::max( sizeU, p.m.size_u0 + 1 );
+  size_t      width = size_t( sizeU ) * S.occRes, height = size_t( sizeV ) * S.occRes;
+  BlockCanvas cv( sizeU, sizeV );
+  for ( auto& p : P ) {
+    OGpa& g  = p.cur;
+    g.occ    = p.occ;
+    g.sizeU0 = p.m.size_u0, g.sizeV0 = p.m.size_v0;
+    if ( p.m.best_match_idx != -1 && hasRef ) {
+      const pccb200_patch& q = ( *S.frames )[f - 1].pl.patches[p.m.best_match_idx].m;
+      g.u0 = q.u0, g.v0 = q.v0, g.orient = q.orientation;
+      placeOne( cv, g.sizeU0, g.sizeV0, g.sizeU0, g.sizeV0, PLACE_MATCHED, g.u0, g.v0, g.orient );
+    } else {
+      placeOne( cv, g.sizeU0, g.sizeV0, g.sizeU0, g.sizeV0, PLACE_BEST_EFFORT, g.u0, g.v0, g.orient );
+    }
+    cv.mark( g.u0, g.v0, g.orient, g.sizeU0, g.sizeV0, p.occ, p.m.size_u0 );
+    extend( g.u0, g.v0, g.orient, g.sizeU0, g.sizeV0, S.occRes, width, height );
+  }
+  S.curW[f] = width, S.curH[f] = height;
+}
+
+// generateGlobalPatches (:7003-7060): extend every live track by its best match in frame f, or end it
+void gpaExtendTracks( GpaState& S, size_t f, Tracks& tracks, size_t preIndex ) {
+  auto& C = ( *S.frames )[f].pl.patches;
+  for ( auto& t : tracks ) {
+    auto& tp = t.second;
+    if ( tp.empty() ) continue;
+    const pccb200_patch& q = ( *S.frames )[tp[preIndex].first].pl.patches[tp[preIndex].second].m;
+    float                best = 0.0F;
+    int                  bestIdx = -1;
+    for ( size_t ci = 0; ci < C.size(); ++ci )
+      if ( q.view_id == C[ci].m.view_id && !C[ci].cur.matched ) {
+        const float iou = rectIou( q, C[ci].m );
+        if ( iou > best ) best = iou, bestIdx = int( ci );
+      }
+    if ( best > 0.2F ) {
+      C[bestIdx].cur.matched = true;
+      tp.emplace_back( f, size_t( bestIdx ) );
+    } else {
+      tp.clear();
+    }
+  }
+  for ( auto& t : tracks )
+    for ( auto& fp : t.second ) {
+      OGpa& g  = ( *S.frames )[fp.first].pl.patches[fp.second].cur;
+      g.global = true, g.track = int( t.first );
+    }
+}
+
+// unionPatchGenerationAndPacking (:7062-7224): one union patch per live track, packed best effort (or with the orientation
+// of the reference frame's matched patch); returns the height of the union packing in pixels
+size_t gpaPackUnions( GpaState& S, const Tracks& tracks, size_t frameWidth, Unions& unions, int refFrame, bool useRef ) {
+  unions.clear();
+  for ( auto& t : tracks ) {
+    if ( t.second.empty() ) continue;
+    UnionPatch U;
+    for ( auto& fp : t.second ) {
+      const pccb200_patch& m = ( *S.frames )[fp.first].pl.patches[fp.second].m;
+      U.sizeU0 = std::max( U.sizeU0, m.size_u0 ), U.sizeV0 = std::max( U.sizeV0, m.size_v0 );
+    }
+    U.occ.assign( size_t( U.sizeU0 ) * U.sizeV0, 0 );
+    U.orient = 0;  // PCCPatch() default
+    if ( useRef ) {
+      const int matched = ( *S.frames )[t.second[0].first].pl.patches[t.second[0].second].m.best_match_idx;
+      U.orient          = matched == -1 ? -1 : ( *S.frames )[refFrame].pl.patches[matched].m.orientation;
+    }
+    for ( auto& fp : t.second ) {
+      const OPatch& p = ( *S.frames )[fp.first].pl.patches[fp.second];
+      for ( int v = 0; v < p.m.size_v0; ++v )
+        for ( int u = 0; u < p.m.size_u0; ++u )
+          if ( p.occ[size_t( v ) * p.m.size_u0 + u] ) U.occ[size_t( v ) * U.sizeU0 + u] = 1;
+    }
+    unions[t.first] = std::move( U );
+  }
+  int sizeU = int( frameWidth ) / S.occRes, sizeV = 0;
+  for ( auto& u : unions ) sizeU = std::max( sizeU, u.second.sizeU0 + 1 ), sizeV = std::max( sizeV, u.second.sizeV0 + 1 );
+  size_t      width = size_t( sizeU ) * S.occRes, height = size_t( sizeV ) * S.occRes;
+  BlockCanvas cv( sizeU, sizeV );
+  for ( auto& it : unions ) {
+    UnionPatch& U = it.second;
+    placeOne( cv, U.sizeU0, U.sizeV0, U.sizeU0, U.sizeV0, !useRef ? PLACE_BEST_EFFORT : ( U.orient != -1 ? PLACE_KNOWN_ORIENTATION : PLACE_STICKY ), U.u0, U.v0,
+              U.orient );
+    cv.mark( U.u0, U.v0, U.orient, U.sizeU0, U.sizeV0, U.occ, U.sizeU0 );
+    extend( U.u0, U.v0, U.orient, U.sizeU0, U.sizeV0, S.occRes, width, height );
+  }
+  return height;
+}
+
+// updateGPAPatchInformation (:7493-7529): global patches take the size of their union (their own occupancy, re-strided)
+void gpaAdoptUnionSizes( GpaState& S, size_t first, size_t second, Unions& unions ) {
+  for ( size_t f = first; f < second; ++f )
+    for ( auto& p : ( *S.frames )[f].pl.patches ) {
+      OGpa& g = p.cur;
+      if ( g.global ) {
+        const UnionPatch& U = unions[size_t( g.track )];
+        g.sizeU0 = U.sizeU0, g.sizeV0 = U.sizeV0;
+        g.occ.assign( size_t( U.sizeU0 ) * U.sizeV0, 0 );
+        for ( int v = 0; v < p.m.size_v0; ++v )
+          for ( int u = 0; u < p.m.size_u0; ++u )
+            if ( p.occ[size_t( v ) * p.m.size_u0 + u] ) g.occ[size_t( v ) * U.sizeU0 + u] = 1;
+      } else {
+        g.sizeU0 = p.m.size_u0, g.sizeV0 = p.m.size_v0, g.occ = p.occ;
+      }
+    }
+}
+
+// performGPAPacking (:7531-7660): global patches at the position of their union, the others packed around them; returns
+// whether this trial packing is rejected
+bool gpaPackSubContext( GpaState& S, size_t first, size_t second, Unions& unions, size_t unionsHeight, bool useRef ) {
+  bool   tooHigh = false;
+  size_t bad     = 0;
+  for ( size_t f = first; f < second; ++f ) {
+    OFrame& F = ( *S.frames )[f];
+    auto&   P = F.pl.patches;
+    if ( P.empty() ) return false;
+    const auto& prevP = ( *S.frames )[f > 0 ? f - 1 : 0].pl.patches;
+    int         sizeU = int( S.frameWidthIn ) / S.occRes;
+    const int   sizeV = int( unionsHeight ) / S.occRes;
+    for ( auto& p : P ) sizeU = std::max( sizeU, p.cur.sizeU0 + 1 );
+    size_t      width = size_t( sizeU ) * S.occRes, height = size_t( sizeV ) * S.occRes;
+    BlockCanvas cv( sizeU, sizeV );
+    for ( auto& p : P ) {
+      OGpa& g = p.cur;
+      if ( !g.global ) continue;
+      const UnionPatch& U = unions[size_t( g.track )];
+      g.u0 = U.u0, g.v0 = U.v0, g.orient = U.orient;
+      cv.mark( g.u0, g.v0, g.orient, g.sizeU0, g.sizeV0, g.occ, g.sizeU0 );
+      extend( g.u0, g.v0, g.orient, g.sizeU0, g.sizeV0, S.occRes, width, height );
+    }
+    for ( auto& p : P ) {
+      OGpa& g = p.cur;
+      if ( g.global ) continue;
+      if ( f == 0 || ( f == first && !useRef ) || p.m.best_match_idx == -1 ) {
+        // packingWithoutRefForFirstFrameNoglobalPatch (:7662-7745) / the unmatched branch of ...WithRef... (:7824-7858)
+        placeOne( cv, g.sizeU0, g.sizeV0, p.m.size_u0, p.m.size_v0, PLACE_BEST_EFFORT, g.u0, g.v0, g.orient );
+      } else {
+        // packingWithRefForFirstFrameNoglobalPatch (:7746-7822): the matched patch's final placement when it lies before the
+        // sub-context, its trial placement otherwise
+        const OPatch& q = prevP[p.m.best_match_idx];
+        if ( f == first ) g.u0 = q.m.u0, g.v0 = q.m.v0, g.orient = q.m.orientation;
+        else g.u0 = q.cur.u0, g.v0 = q.cur.v0, g.orient = q.cur.orient;
+        placeOne( cv, g.sizeU0, g.sizeV0, g.sizeU0, g.sizeV0, PLACE_MATCHED, g.u0, g.v0, g.orient );
+      }
+      cv.mark( g.u0, g.v0, g.orient, g.sizeU0, g.sizeV0, p.occ, p.m.size_u0 );
+      extend( g.u0, g.v0, g.orient, g.sizeU0, g.sizeV0, S.occRes, width, height );
+    }
+    S.curW[f] = width, S.curH[f] = height;
+    if ( height > S.frameHeightIn ) {
+      tooHigh = true;
+      break;
+    }
+    if ( double( height ) / double( F.height ) >= 1.10 ) ++bad;  // BAD_HEIGHT_THRESHOLD
+  }
+  return tooHigh || bad > 2;                                     // BAD_CONDITION_THRESHOLD
+}
+
+// updatePatchInformation (:7358-7491): the accepted (previous) trial becomes the packing of the sub-context [first, second)
+void gpaCommit( GpaState& S, size_t first, size_t second ) {
+  auto& FR = *S.frames;
+  for ( size_t f = first; f < second; ++f ) {
+    FR[f].width = S.preW[f], FR[f].height = S.preH[f];
+    for ( auto& p : FR[f].pl.patches ) {
+      p.m.size_u0 = p.pre.sizeU0, p.m.size_v0 = p.pre.sizeV0, p.occ = p.pre.occ;
+      p.m.u0 = p.pre.u0, p.m.v0 = p.pre.v0, p.m.orientation = p.pre.orient;
+      p.m.is_global = p.pre.global ? 1 : 0;
+    }
+  }
+  if ( second - first == 1 ) {
+    for ( auto& p : FR[first].pl.patches ) p.m.best_match_idx = -1;
+    return;
+  }
+  int globalCount = 0;
+  for ( size_t f = first; f < second; ++f ) {
+    auto& P = FR[f].pl.patches;
+    for ( size_t i = 0; i < P.size(); ++i ) P[i].m.index = int( i );
+    std::vector<OPatch> old = P;
+    globalCount             = 0;
+    for ( auto& p : old ) globalCount += p.m.is_global;
+    P.clear();
+    if ( f == first ) {
+      for ( auto& p : old )
+        if ( p.m.is_global ) P.push_back( p );
+    } else {  // global patches follow the order of the patches they match in the previous frame
+      for ( int i = 0; i < int( FR[f - 1].pl.patches.size() ); ++i )
+        for ( auto& p : old )
+          if ( p.m.best_match_idx == i && p.m.is_global ) {
+            P.push_back( p );
+            break;
+          }
+    }
+    for ( auto& p : old )
+      if ( !p.m.is_global ) P.push_back( p );
+  }
+  for ( size_t f = first; f < second; ++f ) {
+    auto& P = FR[f].pl.patches;
+    for ( int i = 0; i < globalCount; ++i ) {
+      if ( f > first ) P[i].m.best_match_idx = i;
+      P[i].m.index = i;
+    }
+    if ( f == second - 1 ) {
+      for ( int i = globalCount; i < int( P.size() ); ++i ) P[i].m.index = i;
+      continue;
+    }
+    auto&             N = FR[f + 1].pl.patches;
+    std::vector<bool> updated( N.size(), false );
+    for ( int i = globalCount; i < int( P.size() ); ++i ) {
+      for ( int j = globalCount; j < int( N.size() ); ++j )
+        if ( P[i].m.index == N[j].m.best_match_idx && !updated[j] ) {
+          N[j].m.best_match_idx = i;
+          updated[j]            = true;
+          break;
+        }
+      P[i].m.index = i;
+    }
+  }
+  for ( auto& p : FR[first].pl.patches ) p.m.best_match_idx = -1;
+}
+
+void gpaRun( std::vector<OFrame>& frames, int occRes, size_t frameWidthIn, size_t frameHeightIn ) {
+  const size_t n = frames.size();
+  GpaState     S{ &frames, occRes, frameWidthIn, frameHeightIn, std::vector<size_t>( n, 0 ), std::vector<size_t>( n, 0 ), std::vector<size_t>( n, 0 ),
+              std::vector<size_t>( n, 0 ) };
+  size_t       preFirst = 0, preSecond = 0;
+  Tracks       tracks;
+  Unions       unionsCur;
+  bool         start = true;
+  auto clearCur = [&]( size_t a, size_t b ) {
+    for ( size_t j = a; j < b; ++j )
+      for ( auto& p : frames[j].pl.patches ) p.cur.reset();
+  };
+  for ( size_t f = 0; f < n; ++f ) {
+    bool useRef = true;
+    if ( start ) {
+      // initializeSubContext (:6971-6990)
+      preFirst = f, preSecond = f + 1;
+      tracks.clear();
+      auto& P = frames[f].pl.patches;
+      for ( size_t i = 0; i < P.size(); ++i ) {
+        tracks[i].emplace_back( f, i );
+        P[i].cur.global = true, P[i].cur.track = int( i );
+      }
+      if ( preFirst == 0 ) useRef = false;
+      gpaPackFirstFrame( S, f, useRef );
+      S.preW[f] = S.curW[f], S.preH[f] = S.curH[f];
+      S.curW[f] = S.curH[f] = 0;
+      for ( auto& p : P ) {
+        p.pre = p.cur;
+        p.cur.reset();
+      }
+      if ( f == n - 1 ) {
+        gpaCommit( S, preFirst, preSecond );
+        break;
+      }
+      start = false;
+      continue;
+    }
+    const size_t curFirst = preFirst, curSecond = f + 1;
+    int          refFrame = int( curFirst ) - 1;
+    if ( curFirst == 0 ) useRef = false, refFrame = -1;
+    clearCur( curFirst, curSecond );
+    gpaExtendTracks( S, f, tracks, f - curFirst - 1 );
+    const size_t unionsHeight = gpaPackUnions( S, tracks, frames[f].width, unionsCur, refFrame, useRef );
+    bool         badCount = double( unionsCur.size() ) / tracks.size() < 0.15;
+    const bool   badHeight = unionsHeight > frameHeightIn;
+    if ( unionsHeight == 0 ) badCount = true;
+    bool badPacking = false;
+    if ( !badCount && !badHeight ) {
+      gpaAdoptUnionSizes( S, curFirst, curSecond, unionsCur );
+      badPacking = gpaPackSubContext( S, curFirst, curSecond, unionsCur, unionsHeight, useRef );
+    }
+    if ( badCount || badHeight || badPacking ) {
+      clearCur( curFirst, curSecond );
+      unionsCur.clear();
+      tracks.clear();
+      start = true;
+      --f;  // the frame that broke the sub-context opens the next one
+      gpaCommit( S, preFirst, preSecond );
+    } else {
+      for ( size_t j = curFirst; j < curSecond; ++j ) {
+        S.preW[j] = S.curW[j], S.preH[j] = S.curH[j];
+        for ( auto& p : frames[j].pl.patches ) p.pre = p.cur;
+      }
+      preFirst = curFirst, preSecond = curSecond;
+      clearCur( curFirst, curSecond );
+      unionsCur.clear();
+      if ( f == n - 1 ) {
+        gpaCommit( S, preFirst, preSecond );
+        break;
+      }
+    }
+  }
+}
+
 // weighted mean used by the push-pull filter (PCCEncoder.cpp:6357-6369)
 inline int mean4w( int p1, int w1, int p2, int w2, int p3, int w3, int p4, int w4 ) {
   return ( p1 * w1 + p2 * w2 + p3 * w3 + p4 * w4 ) / ( w1 + w2 + w3 + w4 );
@@ -1044,7 +1491,15 @@ void* pcco_encode_gof_canvas( int nframes, const int16_t* const* xyz, const uint
     G->frames[f].pl = std::move( *pl );
     delete pl;
     G->frames[f].height = minH;
-    packFrame( G->frames[f], occRes, minW, 2, 1.0 );
+    if ( f == 0 || prm->global_patch_allocation == 0 ) packFrame( G->frames[f], occRes, minW, 2, 1.0 );
+    else packFrameAfter( G->frames[f], G->frames[f - 1], occRes, minW, 2, 1.0 );
+  }
+  if ( prm->global_patch_allocation != 0 && nframes > 0 && !G->frames[0].pl.patches.empty() && !getenv( "PCCO_DEBUG_NO_GPA" ) ) {
+    // PCCEncoder::placeSegments (:4807-4827): common tile size, global patch allocation over the GOF, common tile size again
+    size_t tw = minW, th = minH;
+    for ( auto& F : G->frames ) tw = std::max( tw, F.width ), th = std::max( th, F.height );
+    for ( auto& F : G->frames ) F.width = tw, F.height = th;
+    gpaRun( G->frames, occRes, minW, minH );
   }
   // ---- a14: one canvas size for the GOF (resizeTileGeometryVideo + resizeGeometryVideo, PCCEncoder.cpp:5546-5634)
   size_t W = minW, H = minH;

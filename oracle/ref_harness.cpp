@@ -132,6 +132,8 @@ void fillPatch( const PCCPatch& s, pccb200_patch& d, int64_t depthOff, int64_t o
   d.orientation      = int32_t( s.getPatchOrientation() );
   d.d0_count         = int32_t( s.getD0Count() );
   d.eom_and_d1_count = int32_t( s.getEOMandD1Count() );
+  d.best_match_idx   = int32_t( s.getBestMatchIdx() );
+  d.is_global        = s.getIsGlobalPatch() ? 1 : 0;
   d.depth_offset     = depthOff;
   d.occ_offset       = occOff;
 }
@@ -367,8 +369,8 @@ void setCtcParams( PCCEncoderParameters& ep, const pccb200_seg_params& p, int oc
   ep.enablePointCloudPartitioning_        = false;
   ep.enhancedOccupancyMapCode_            = false;
   ep.profileReconstructionIdc_            = 1;
-  ep.constrainedPack_                     = false;
-  ep.globalPatchAllocation_               = 0;
+  ep.constrainedPack_                     = p.global_patch_allocation != 0;  // (cfg/condition/ctc-random-access.cfg keeps the default 1)
+  ep.globalPatchAllocation_               = p.global_patch_allocation;
   ep.nbThread_                            = 1;
   ep.groupOfFramesSize_                   = 32;
   ep.compressedStreamPath_                = "/tmp/pccb200_ref_harness.bin";

@@ -25,7 +25,7 @@ class SegParams(C.Structure):
         "voxel_dim_refine", "search_radius_refine", "occupancy_resolution", "enable_patch_splitting",
         "max_patch_size", "quantizer_size_x", "quantizer_size_y", "min_point_count_per_cc",
         "max_nn_count_patch_seg", "surface_thickness", "min_level", "max_allowed_depth",
-        "geometry_bitdepth_2d", "geometry_bitdepth_3d", "map_count_minus1", "reserved0")] + [
+        "geometry_bitdepth_2d", "geometry_bitdepth_3d", "map_count_minus1", "global_patch_allocation")] + [
         ("lambda_refine", C.c_double), ("max_allowed_dist2_raw_detection", C.c_double),
         ("max_allowed_dist2_raw_selection", C.c_double), ("weight_normal", C.c_double * 3)]
 
@@ -65,11 +65,11 @@ class Patch(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "index", "view_id", "normal_axis", "tangent_axis", "bitangent_axis", "projection_mode",
         "u1", "v1", "d1", "size_u", "size_v", "size_d", "size_d_pixel", "size_u0", "size_v0",
-        "size_2d_x", "size_2d_y", "u0", "v0", "orientation", "d0_count", "eom_and_d1_count")] + [
+        "size_2d_x", "size_2d_y", "u0", "v0", "orientation", "d0_count", "eom_and_d1_count", "best_match_idx", "is_global")] + [
         ("depth_offset", C.c_int64), ("occ_offset", C.c_int64)]
 
 
-PATCH_DTYPE = np.dtype([(n, np.int32) for n, _ in Patch._fields_[:22]] + [("depth_offset", np.int64), ("occ_offset", np.int64)])
+PATCH_DTYPE = np.dtype([(n, np.int32) for n, _ in Patch._fields_[:24]] + [("depth_offset", np.int64), ("occ_offset", np.int64)])
 assert PATCH_DTYPE.itemsize == C.sizeof(Patch)
 
 
@@ -234,6 +234,15 @@ class Oracle:
         h = self.lib.pcco_segment_patches(ptr(xyz, c_i16p), ptr(rgb, c_u8p), len(xyz), ptr(nbr, c_u32p), nbr.shape[1],
                                           ptr(part, c_u8p), C.byref(params))
         return _collect_patches(self.lib, "pcco_", h)
+
+
+    def segment_frame_patches(self, xyz, rgb, params):
+        """a1..a11 of one frame: the patch list in creation order (PatchSet)"""
+        xyz = _xyz(xyz)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        self.lib.pcco_segment_frame.restype = C.c_void_p
+        self.lib.pcco_segment_frame.argtypes = [c_i16p, c_u8p, C.c_size_t, C.POINTER(SegParams)]
+        return _collect_patches(self.lib, "pcco_", self.lib.pcco_segment_frame(ptr(xyz, c_i16p), ptr(rgb, c_u8p), len(xyz), C.byref(params)))
 
 
 # --------------------------------------------------------------------------------------------- reference

@@ -125,3 +125,27 @@ def random_cloud(n=2000, span=64, seed=0):
     rng = np.random.default_rng(seed)
     xyz = _unique_rows(rng.integers(0, span, size=(n * 2, 3)).astype(np.int16))[:n]
     return xyz, _texture(xyz, seed)
+
+
+def sheet_stack(layers=14, frame=0, seed=0, spacing=3, extent=126, gap=14):
+    """Packing stress (random-access / global patch allocation): 9 x `layers` sparse square sheets, each its own connected
+    component and an (extent/16)^2-block patch, jittered and resized from frame to frame so that patch unions grow and the
+    packed canvas exceeds the minimum image height. Few points per occupancy block keep segmentation cheap."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 4, size=(3, 3, layers, 2))          # per-sheet origin jitter (fixed over time)
+    grow = rng.integers(0, 3, size=(3, 3, layers))
+    parts = []
+    for ix in range(3):
+        for iy in range(3):
+            for iz in range(layers):
+                e = extent + 16 * int((grow[ix, iy, iz] + frame * (1 + (ix + iy + iz) % 2)) % 3) - 16
+                g = np.arange(0, e, spacing)
+                a, b = np.meshgrid(g, g, indexing="ij")
+                a, b = a.ravel(), b.ravel()
+                ox = 8 + ix * 170 + int(base[ix, iy, iz, 0]) + (frame * (1 + iz % 3)) % 5
+                oy = 8 + iy * 170 + int(base[ix, iy, iz, 1]) + (frame * (1 + ix % 2)) % 4
+                oz = 6 + iz * gap
+                parts.append(np.stack([a + ox, b + oy, np.full_like(a, oz)], 1))
+    xyz = _unique_rows(np.concatenate(parts).astype(np.int16))
+    xyz = xyz[np.random.default_rng(seed + frame).permutation(len(xyz))]
+    return xyz, _texture(xyz, seed + frame)
