@@ -34,6 +34,11 @@ def test_oracle_matches_golden_fixture(oracle):
     for f, (a, b) in enumerate(zip(got, gold["frames"])):
         for k in b:
             assert a[k] == b[k], "frame %d product %s differs from the reference fixture" % (f, k)
+    ra = m.golden_ra_frames()
+    got = m.products_digest(oracle.encode_gof(ra, m.golden_ra_params(oracle, ra), occupancy_precision=2))
+    for f, (a, b) in enumerate(zip(got, gold["frames_random_access_r5"])):
+        for k in b:
+            assert a[k] == b[k], "random-access frame %d product %s differs from the reference fixture" % (f, k)
     xyz = synth.planes(n_side=20)[0]
     idx, d = oracle.knn(xyz, xyz, 16)
     assert m.digest(idx) == gold["knn16_planes20"]["idx"] and m.digest(d) == gold["knn16_planes20"]["dist"]

@@ -115,3 +115,20 @@ def test_gpu_ra_gof_vs_oracle(name, oracle, product):
     got = product.encode_gof(frames, prm, occupancy_precision=2, stop_after=stop)
     want = oracle.encode_gof(frames, prm, occupancy_precision=2, stop_after=stop)
     assert bindings.compare_gof(got, want) == []
+
+
+@pytest.mark.gpu
+def test_gpu_ra_gof_vs_reference_fixture(product):
+    """the committed fixture was generated from the reference itself (tests/golden/make_golden.py): every product digest must match"""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    with open(os.path.join(ROOT, "tests", "golden", "gof_small.json")) as f:
+        gold = json.load(f)["frames_random_access_r5"]
+    frames = m.golden_ra_frames()
+    got = m.products_digest(product.encode_gof(frames, m.golden_ra_params(product, frames), occupancy_precision=2))
+    for f, (a, b) in enumerate(zip(got, gold)):
+        for k in b:
+            assert a[k] == b[k], "random-access frame %d product %s differs from the reference fixture" % (f, k)
