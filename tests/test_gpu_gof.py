@@ -75,3 +75,23 @@ def test_lossy_codec_round_trip_protocol(oracle, product):
     ref = product.generate_point_cloud(one_shot[0].patches.patches, om, noisy0, noisy1, W, H)
     assert np.array_equal(rec, ref["xyz"].ravel()) and np.array_equal(p2p, ref["point_to_pixel"].ravel())
     assert not np.array_equal(rec, one_shot[0][bindings.GOF_REC_XYZ])
+
+
+def test_encode_gof_vs_reference_fixture(product):
+    """tests/golden/gof_small.json holds digests of every product as computed by the reference itself (make_golden.py)"""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(root, "tests", "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    with open(os.path.join(root, "tests", "golden", "gof_small.json")) as f:
+        gold = json.load(f)
+    frames = m.golden_frames()
+    prm = m.golden_params(product, frames)
+    assert [float(x) for x in prm.weight_normal] == gold["weight_normal"]
+    got = m.products_digest(product.encode_gof(frames, prm))
+    for f, (a, b) in enumerate(zip(got, gold["frames"])):
+        for k in b:
+            assert a[k] == b[k], "frame %d product %s differs from the reference fixture" % (f, k)
