@@ -57,6 +57,14 @@ __global__ void kResetMinMax( SlotView sv, int numSlots ) {
   sv.at( F_DIVHIGH, s ) = INT_MAX;
 }
 
+// same-address extremes: read (L2) before the atomic; a stale value can only cause a redundant atomic (see patches.cu relaxMin)
+__device__ __forceinline__ void relaxMin( int* addr, int v ) {
+  if ( v < __ldcg( addr ) ) atomicMin( addr, v );
+}
+__device__ __forceinline__ void relaxMax( int* addr, int v ) {
+  if ( v > __ldcg( addr ) ) atomicMax( addr, v );
+}
+
 // step 1: min/max per slot and dimension. Consecutive positions almost always share a slot, so a warp first
 // agrees on one slot and reduces with redux.sync; mixed warps fall back to per-lane atomics.
 __global__ void kMinMax( SlotView sv, const short4* __restrict__ pts, const uint32_t* __restrict__ vind,
@@ -75,15 +83,15 @@ __global__ void kMinMax( SlotView sv, const short4* __restrict__ pts, const uint
     for ( int d = 0; d < 3; ++d ) {
       int mn = __reduce_min_sync( act, v[d] ), mx = __reduce_max_sync( act, v[d] );
       if ( ( threadIdx.x & 31 ) == leader ) {
-        atomicMin( &sv.at( F_MM + d, s ), mn );
-        atomicMax( &sv.at( F_MM + 3 + d, s ), mx );
+        relaxMin( &sv.at( F_MM + d, s ), mn );
+        relaxMax( &sv.at( F_MM + 3 + d, s ), mx );
       }
     }
   } else {
 #pragma unroll
     for ( int d = 0; d < 3; ++d ) {
-      atomicMin( &sv.at( F_MM + d, s ), v[d] );
-      atomicMax( &sv.at( F_MM + 3 + d, s ), v[d] );
+      relaxMin( &sv.at( F_MM + d, s ), v[d] );
+      relaxMax( &sv.at( F_MM + 3 + d, s ), v[d] );
     }
   }
 }
@@ -257,15 +265,15 @@ __global__ void kDivsAndAssign( SlotView sv, const short4* __restrict__ pts, con
     int r = side == 0 ? __reduce_max_sync( act, v ) : __reduce_min_sync( act, v );
     if ( ( threadIdx.x & 31 ) == leader ) {
       if ( side == 0 )
-        atomicMax( &sv.at( F_DIVLOW, s ), r );
+        relaxMax( &sv.at( F_DIVLOW, s ), r );
       else
-        atomicMin( &sv.at( F_DIVHIGH, s ), r );
+        relaxMin( &sv.at( F_DIVHIGH, s ), r );
     }
   } else {
     if ( side == 0 )
-      atomicMax( &sv.at( F_DIVLOW, s ), v );
+      relaxMax( &sv.at( F_DIVLOW, s ), v );
     else
-      atomicMin( &sv.at( F_DIVHIGH, s ), v );
+      relaxMin( &sv.at( F_DIVHIGH, s ), v );
   }
 }
 

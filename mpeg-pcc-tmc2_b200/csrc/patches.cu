@@ -182,6 +182,16 @@ __global__ void kMembers( const uint32_t* __restrict__ label, const uint32_t* __
   }
 }
 
+// atomicMin / atomicMax on a per-patch extreme that ~10^4 points share: a plain (L2) read first - the stored value only ever
+// moves towards the extreme, so a stale read can at worst cost a redundant atomic, never skip a needed one. Almost every point
+// is inside the box the first few have spanned, which takes the serialised same-address atomics off the critical path.
+__device__ __forceinline__ void relaxMin( int* addr, int v ) {
+  if ( v < __ldcg( addr ) ) atomicMin( addr, v );
+}
+__device__ __forceinline__ void relaxMax( int* addr, int v ) {
+  if ( v > __ldcg( addr ) ) atomicMax( addr, v );
+}
+
 __global__ void kMinUV( const short4* __restrict__ pts, const uint8_t* __restrict__ partition, const int* __restrict__ member, int n,
                         PatchStats* stats ) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,8 +200,8 @@ __global__ void kMinUV( const short4* __restrict__ pts, const uint8_t* __restric
   if ( m < 0 ) return;
   const int    view = partition[stats[m].seed];
   const short4 p    = pts[i];
-  atomicMin( &stats[m].minU, axisOf( p, cViewAxes[view][1] ) );
-  atomicMin( &stats[m].minV, axisOf( p, cViewAxes[view][2] ) );
+  relaxMin( &stats[m].minU, axisOf( p, cViewAxes[view][1] ) );
+  relaxMin( &stats[m].minV, axisOf( p, cViewAxes[view][2] ) );
 }
 
 __global__ void kSplitAndBounds( const short4* __restrict__ pts, const uint8_t* __restrict__ partition, int* __restrict__ member, int n,
@@ -209,8 +219,8 @@ __global__ void kSplitAndBounds( const short4* __restrict__ pts, const uint8_t* 
       return;
     }
   }
-  atomicMin( &stats[m].bbMin[0], int( p.x ) ), atomicMin( &stats[m].bbMin[1], int( p.y ) ), atomicMin( &stats[m].bbMin[2], int( p.z ) );
-  atomicMax( &stats[m].bbMax[0], int( p.x ) ), atomicMax( &stats[m].bbMax[1], int( p.y ) ), atomicMax( &stats[m].bbMax[2], int( p.z ) );
+  relaxMin( &stats[m].bbMin[0], int( p.x ) ), relaxMin( &stats[m].bbMin[1], int( p.y ) ), relaxMin( &stats[m].bbMin[2], int( p.z ) );
+  relaxMax( &stats[m].bbMax[0], int( p.x ) ), relaxMax( &stats[m].bbMax[1], int( p.y ) ), relaxMax( &stats[m].bbMax[2], int( p.z ) );
 }
 
 __global__ void kFillU64( unsigned long long* p, size_t n, unsigned long long v ) {

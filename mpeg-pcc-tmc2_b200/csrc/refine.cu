@@ -514,7 +514,11 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
   kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 1, sc.list, ctl );
   // Four launches per sweep and no host round trip: the sweep's work list lives on the device (see kSmoothAndMark).
   const int iterations = std::max( 1, prm.iteration_count_refine );
-  const int sweepCtas  = int( std::min<size_t>( divUp( V, 4 ), 148 * 4 ) );
+  static const int ctasPerSm = [] {  // (tuning knob; 4 x 128 threads per SM leaves room for the other frames' kernels)
+    const char* e = getenv( "PCCB200_SWEEP_CTAS_PER_SM" );
+    return e && atoi( e ) > 0 ? atoi( e ) : 4;
+  }();
+  const int sweepCtas  = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * ctasPerSm ) );
   for ( int it = 0; it < iterations; ++it ) {
     kInitialActive<<<divUp( V, 256 ), 256, 0, s>>>( st, V, sc.list, ctl );
     kSmoothAndMark<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.smooth );
