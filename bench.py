@@ -3,11 +3,15 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--frames F] [--scale S]
 
-One "step" = one GOF-sized batch of F synthetic longdress-like frames (tests/synth.py `figure`, 10-bit, ≈0.83 M points
+One "step" = one GOF (--frames F frames per GPU) of synthetic longdress-like frames (tests/synth.py `figure`, 10-bit, ≈0.83 M points
 per frame at the default scale) pushed through the whole hot path: generateSegments, placeSegments, occupancy / geometry
 image formation, generatePointCloud, colour transfer, attribute image formation and padding (PCCEncoder.cpp:103-424,
 the three videoEncoder.compress calls excluded, occupancy/geometry video treated as lossless).  No dataset ships with
 the reference, so the data is synthetic and says so.
+
+Steps are independent GOFs; --gofs-in-flight of them are processed concurrently (one library context each, started staggered):
+the orientation walk of a frame is a 1-2 s single-warp latency chain, so the GPU is kept busy by the data-parallel stages of
+the other GOFs in flight. value / e2e are whole-job throughputs over the timed region (K GOFs, barrier to barrier).
 
 Multi-GPU (torchrun, one process per GPU): the frames of every GOF are sharded over the ranks (rank r takes F frames of
 an N*F-frame GOF: weak scaling); the one cross-frame coupling of the all-intra path — the common canvas size — is one
@@ -129,7 +133,8 @@ def config(args, npts, frames_per_rank, world):
                       "packing, occupancy/geometry images + dilation, generatePointCloud, colour transfer, attribute images, push-pull padding",
             "excluded": "ply load, videoEncoder.compress x3, post-processing, bitstream (as in BASELINE.md §4)",
             "frames_in_flight": frames_per_rank * max(1, min(args.gofs_in_flight, args.steps)), "gofs_in_flight": max(1, min(args.gofs_in_flight, args.steps)), "host_cores": host_cores(), "parallelism": "frames of a GOF sharded over %d GPU(s)" % world,
-            "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2"}
+            "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2",
+            "host_buffers": "pinned (inputs and the frames handed to the video codec)", "scratch_sets": args.scratch_sets}
 
 
 def run_reference(args, frames, prm):
@@ -171,14 +176,14 @@ def run_reference(args, frames, prm):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frames per step and GPU (a GOF is 32 frames)")
     ap.add_argument("--scale", type=float, default=0.626, help="figure scale; 0.626 gives ~0.83 Mpts/frame like longdress_vox10")
     ap.add_argument("--iterations", type=int, default=50, help="iterationCountRefineSegmentation (longdress cfg: 50)")
     ap.add_argument("--ref-frames", type=int, default=32, help="frames per step of the reference arm (one host process per frame, up to the core count)")
-    ap.add_argument("--gofs-in-flight", type=int, default=6, help="GOFs processed concurrently (each on its own context); steps are independent GOFs")
+    ap.add_argument("--gofs-in-flight", type=int, default=8, help="GOFs processed concurrently (each on its own context); steps are independent GOFs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", default=None, help="write the last GOF's per-frame stage spans (name, start ms, ms) to this JSON file")
     ap.add_argument("--scratch-sets", type=int, default=24, help="scratch sets of the device pool = frames inside the data-parallel stage groups at once")
@@ -220,7 +225,7 @@ def main():
     for p in prods:
         p.profile(True)
     total_pts = sum(len(f[0]) for f in frames)
-    outbufs = [dict() for _ in range(lanes)]
+    outbuf, outlock = dict(), threading.Lock()   # ONE set of pinned hand-off buffers: the lanes take turns copying out (45 ms per GOF)
 
     def phase_a(lane):
         """a1..a13 of one GOF: segmentation (incl. the orientation walk) + packing"""
@@ -230,18 +235,19 @@ def main():
 
     def phase_b(lane, g, t0, W, H):
         """a16..a26 + hand-off: images, reconstruction, colour, attribute images; D2H of every frame the codec would receive"""
-        p, outbuf = prods[lane], outbufs[lane]
+        p = prods[lane]
         t0, ta = t0
         g.resume(W, H, 0)
         t1 = time.perf_counter()
         nbytes = 0
-        for f in range(len(frames)):
-            for what in HANDOFF:
-                cnt = g.count(f, what)
-                if (f, what) not in outbuf or outbuf[(f, what)].size != cnt:
-                    outbuf[(f, what)] = pinned((cnt,), bindings.GOF_DTYPES[what])
-                g.fetch(f, what, outbuf[(f, what)])
-                nbytes += outbuf[(f, what)].nbytes
+        with outlock:
+            for f in range(len(frames)):
+                for what in HANDOFF:
+                    cnt = g.count(f, what)
+                    if (f, what) not in outbuf or outbuf[(f, what)].size != cnt:
+                        outbuf[(f, what)] = pinned((cnt,), bindings.GOF_DTYPES[what])
+                    g.fetch(f, what, outbuf[(f, what)])
+                    nbytes += outbuf[(f, what)].nbytes
         t2 = time.perf_counter()
         spans = p.profile_read()
         g.free()
@@ -373,8 +379,9 @@ def main():
             lc = json.load(f)
         out["gpu_launches"] = int(lc.get("launches_per_frame", 0) * args.frames * args.steps)
         out["gpu_launches_source"] = lc.get("source")
-        if lc.get("traffic_bytes_per_launch", {}).get(dom):
-            out["roofline"]["traffic"] = lc["traffic_bytes_per_launch"][dom]
+        if lc.get("traffic_bytes_per_frame", {}).get(dom):   # ncu --set full of the kernel on ONE frame; a launch covers per_launch frames
+            out["roofline"]["traffic"] = int(lc["traffic_bytes_per_frame"][dom] * per_launch)
+            out["roofline"]["traffic_source"] = lc.get("traffic_source")
     if not args.no_cpu_baseline and os.path.exists(bindings.REF_SO):
         ref = bindings.Reference()
         t0 = time.perf_counter()

@@ -241,11 +241,7 @@ __global__ void kRecount( VoxState st, const uint32_t* __restrict__ voxStart, co
   if ( v < 3 ) ctl[v] = 0;
   if ( v >= V ) return;
   list[v] = kNoEntry;
-  uint16_t       sc[6] = {0, 0, 0, 0, 0, 0};
   const uint32_t s = voxStart[v], c = voxCount[v];
-  for ( uint32_t j = 0; j < c; ++j ) ++sc[partition[idsSorted[s + j]]];
-#pragma unroll
-  for ( int k = 0; k < 6; ++k ) st.score[size_t( v ) * 8 + k] = sc[k];
   uint8_t edge = st.edge[v];
   bool    dirty = st.dirty[v] != 0;
   if ( initialise ) {
@@ -254,7 +250,11 @@ __global__ void kRecount( VoxState st, const uint32_t* __restrict__ voxStart, co
   } else if ( st.mark[v] && edge == NO_EDGE ) {
     edge = INDIRECT_EDGE;
   }
-  if ( dirty ) {
+  if ( dirty ) {  // (only a relabelled voxel has a new histogram: the others keep their row)
+    uint16_t sc[6] = {0, 0, 0, 0, 0, 0};
+    for ( uint32_t j = 0; j < c; ++j ) ++sc[partition[idsSorted[s + j]]];
+#pragma unroll
+    for ( int k = 0; k < 6; ++k ) st.score[size_t( v ) * 8 + k] = sc[k];
     if ( edge != S_DIRECT_EDGE ) {
       int used = 0;
 #pragma unroll
@@ -297,7 +297,7 @@ __device__ __forceinline__ unsigned ldVolatile( const unsigned* p ) { return *re
 __global__ void __launch_bounds__( 128 )
     kSmoothAndMark( VoxState st, uint32_t* __restrict__ list, unsigned* __restrict__ ctl, const uint32_t* __restrict__ adjOff,
                     const uint32_t* __restrict__ adjLen, const uint32_t* __restrict__ adjData, const uint32_t* __restrict__ nearData,
-                    const uint8_t* __restrict__ nearLen, uint16_t* __restrict__ smooth ) {
+                    const uint8_t* __restrict__ nearLen, uint16_t* __restrict__ smooth, unsigned maxSleepNs ) {
   const int lane = threadIdx.x & 31;
   for ( ;; ) {
     unsigned w = 0;
@@ -305,6 +305,7 @@ __global__ void __launch_bounds__( 128 )
     w          = __shfl_sync( 0xffffffffu, w, 0 );
     uint32_t v = kNoEntry;
     if ( lane == 0 ) {
+      unsigned nap = 128;  // (the waiters poll L2: back off, the other frames' kernels share it)
       for ( ;; ) {
         const unsigned c0 = ldVolatile( &ctl[0] );
         if ( w < c0 ) {
@@ -313,7 +314,8 @@ __global__ void __launch_bounds__( 128 )
         }
         const unsigned done = ldVolatile( &ctl[2] );
         if ( done == c0 && ldVolatile( &ctl[0] ) == c0 ) break;  // quiescent: all reserved entries finished, none in flight
-        __nanosleep( 100 );
+        __nanosleep( nap );
+        nap = min( nap * 2, maxSleepNs );
       }
     }
     v = __shfl_sync( 0xffffffffu, v, 0 );
@@ -519,9 +521,13 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
     return e && atoi( e ) > 0 ? atoi( e ) : 4;
   }();
   const int sweepCtas  = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * ctasPerSm ) );
+  static const unsigned maxSleepNs = [] {
+    const char* e = getenv( "PCCB200_SWEEP_MAX_SLEEP_NS" );
+    return unsigned( e && atoi( e ) > 0 ? atoi( e ) : 2048 );
+  }();
   for ( int it = 0; it < iterations; ++it ) {
     kInitialActive<<<divUp( V, 256 ), 256, 0, s>>>( st, V, sc.list, ctl );
-    kSmoothAndMark<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.smooth );
+    kSmoothAndMark<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.smooth, maxSleepNs );
     kRelabel<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.smooth, sc.weight, sc.voxStart, sc.voxCount, sc.idsSorted, normals, partition );
     kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 0, sc.list, ctl );
     PCC_LAUNCH_CHECK();
