@@ -169,7 +169,7 @@ def run_reference(args, frames, prm):
             "warmup": args.warmup_ref, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16/f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": "Mpoints/s", "cores": cores, "kind": "reference",
-                             "sample": "%d frame(s) of the workload per step, one per host core" % cores},
+                             "sample": "%d frame(s) of the workload per step, one per host core (%d timed step(s) after %d warm-up)" % (cores, args.steps_ref, args.warmup_ref)},
             "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -188,7 +188,8 @@ def main():
     ap.add_argument("--timeline", default=None, help="write the last GOF's per-frame stage spans (name, start ms, ms) to this JSON file")
     ap.add_argument("--scratch-sets", type=int, default=24, help="scratch sets of the device pool = frames inside the data-parallel stage groups at once")
     args = ap.parse_args()
-    args.steps_ref, args.warmup_ref = 1, 0
+    # reference arm: every step is a bounded sample (one frame per host core, ~15 s); a few steps keep the run within minutes
+    args.steps_ref, args.warmup_ref = max(1, min(args.steps, 3)), min(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
