@@ -197,7 +197,12 @@ enum {
   PCCB200_GOF_ATTR0_RAW      = 11, /* uint16 3*W*H planar R,G,B: attribute frame 2f   before padding                        */
   PCCB200_GOF_ATTR1_RAW      = 12, /* uint16 3*W*H        attribute frame 2f+1 before padding                               */
   PCCB200_GOF_ATTR0          = 13, /* uint16 3*W*H        attribute frame 2f   after push-pull padding (-> colour conversion -> HM) */
-  PCCB200_GOF_ATTR1          = 14  /* uint16 3*W*H        attribute frame 2f+1 after push-pull padding                      */
+  PCCB200_GOF_ATTR1          = 14, /* uint16 3*W*H        attribute frame 2f+1 after push-pull padding                      */
+  /* the padded attribute frames as PCCVideoEncoder::compress hands them to the codec (PccLibEncoder/source/PCCVideoEncoder.cpp:
+   * 326-353): RGB444 -> YUV 4:2:0, 8 bit, PCCInternalColorConverter "RGB444ToYUV420_8_4" (the default down-sampling filter).
+   * Planes Y (W*H), U, V ((W/2)*(H/2) each); converted on the device when requested: a quarter of the bytes of ATTR0/ATTR1. */
+  PCCB200_GOF_ATTR0_YUV420   = 15, /* uint8  W*H*3/2 */
+  PCCB200_GOF_ATTR1_YUV420   = 16  /* uint8  W*H*3/2 */
 };
 size_t pccb200_gof_get( pccb200_gof* gof, int f, int what, void* dst );
 

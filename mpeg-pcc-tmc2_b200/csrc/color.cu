@@ -109,4 +109,82 @@ void transferColors( ColorScratch& sc, const KdTree& srcTree, const short4* srcP
   PCC_LAUNCH_CHECK();
 }
 
+// ---- §8f-2: RGB444 -> YUV 4:2:0 (8 bit) of a padded attribute frame, as PCCVideoEncoder::compress converts it before the
+// codec (PccLibEncoder/source/PCCVideoEncoder.cpp:326-353 -> PCCInternalColorConverter "RGB444ToYUV420_8_4":
+// PccLibColorConverter/source/PCCInternalColorConverter.cpp:407-424, 553-593, 642-666, filters
+// PccLibColorConverter/include/PCCInternalColorConverter.h:153-183). Doing it here keeps the frame on the device until it has
+// its final 1.5 bytes per pixel instead of 6. Arithmetic as the reference: float samples, double accumulation in tap order, one
+// rounding to float per stage (no fused multiply-add: the library is built with -fmad=false).
+namespace {
+// down-sampling filter 4 (DF_GS), the default of PCCVideoEncoder::compress: the reference's constants, float( c * 512 ), shift 9
+__constant__ float cGsHor[15] = {float( -0.01716352771649 * 512 ), float( 0.0 ), float( +0.04066666714886 * 512 ), float( 0.0 ),
+                                 float( -0.09154810319329 * 512 ), float( 0.0 ), float( 0.31577823859943 * 512 ), float( 0.50453345032298 * 512 ),
+                                 float( 0.31577823859943 * 512 ), float( 0.0 ), float( -0.09154810319329 * 512 ), float( 0.0 ),
+                                 float( 0.04066666714886 * 512 ), float( 0.0 ), float( -0.01716352771649 * 512 )};
+__constant__ float cGsVer[16] = {float( -0.00945406160902 * 512 ), float( -0.01539537217249 * 512 ), float( 0.02360533018213 * 512 ),
+                                 float( 0.03519540819902 * 512 ), float( -0.05254456550808 * 512 ), float( -0.08189331229717 * 512 ),
+                                 float( 0.14630826357715 * 512 ), float( 0.45417830962846 * 512 ), float( 0.45417830962846 * 512 ),
+                                 float( 0.14630826357715 * 512 ), float( -0.08189331229717 * 512 ), float( -0.05254456550808 * 512 ),
+                                 float( 0.03519540819902 * 512 ), float( 0.02360533018213 * 512 ), float( -0.01539537217249 * 512 ),
+                                 float( -0.00945406160902 * 512 )};
+
+__device__ __forceinline__ uint8_t quantise8( float v, bool chroma ) {  // floatYUVToYUV, one byte per sample
+  float r = roundf( float( 255. * double( v ) + ( chroma ? 128. : 0. ) ) );
+  r       = fminf( fmaxf( r, 0.f ), 255.f );
+  return uint8_t( r );
+}
+
+__global__ void kRgbToYuv444( const uint16_t* __restrict__ rgb, size_t Q, uint8_t* __restrict__ outY, float* __restrict__ U, float* __restrict__ V ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i >= Q ) return;
+  const float  r = float( rgb[i] ) / 255.f, g = float( rgb[Q + i] ) / 255.f, b = float( rgb[2 * Q + i] ) / 255.f;
+  const double y = 0.212600 * r + 0.715200 * g + 0.072200 * b, u = -0.114572 * r - 0.385428 * g + 0.500000 * b,
+               v = 0.500000 * r - 0.454153 * g - 0.045847 * b;
+  outY[i] = quantise8( float( y < 0.0 ? 0.0 : ( y > 1.0 ? 1.0 : y ) ), false );
+  U[i]    = float( u < -0.5 ? -0.5 : ( u > 0.5 ? 0.5 : u ) );
+  V[i]    = float( v < -0.5 ? -0.5 : ( v > 0.5 ? 0.5 : v ) );
+}
+// horizontal pass of both chroma planes (blockIdx.z selects the plane): W x H -> W/2 x H
+__global__ void kChromaDownH( const float* __restrict__ U, const float* __restrict__ V, int W, int H, float* __restrict__ tU, float* __restrict__ tV ) {
+  const int    w2 = W / 2;
+  const size_t t  = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( t >= size_t( w2 ) * H ) return;
+  const float* in  = blockIdx.z ? V : U;
+  float*       out = blockIdx.z ? tV : tU;
+  const int    i = int( t / w2 ), j = int( t % w2 );
+  double       acc = 0;
+#pragma unroll
+  for ( int k = 0; k < 15; ++k ) {
+    const int x = min( max( 2 * j + k - 7, 0 ), W - 1 );
+    acc         = acc + double( cGsHor[k] ) * double( in[size_t( i ) * W + x] );
+  }
+  out[t] = float( ( acc + 0.0 ) * double( 1.0f / 512.f ) );
+}
+// vertical pass + quantisation: W/2 x H -> W/2 x H/2 bytes
+__global__ void kChromaDownV( const float* __restrict__ tU, const float* __restrict__ tV, int w2, int H, uint8_t* __restrict__ outU, uint8_t* __restrict__ outV ) {
+  const int    h2 = H / 2;
+  const size_t t  = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( t >= size_t( w2 ) * h2 ) return;
+  const float* in  = blockIdx.z ? tV : tU;
+  uint8_t*     out = blockIdx.z ? outV : outU;
+  const int    i = int( t / w2 ), j = int( t % w2 );
+  double       acc = 0;
+#pragma unroll
+  for ( int k = 0; k < 16; ++k ) {
+    const int y = min( max( 2 * i + k - 7, 0 ), H - 1 );
+    acc         = acc + double( cGsVer[k] ) * double( in[size_t( y ) * w2 + j] );
+  }
+  out[t] = quantise8( float( ( acc + 0.0 ) * double( 1.0f / 512.f ) ), true );
+}
+}  // namespace
+
+void rgbPlanesToYuv420( const uint16_t* rgbPlanes, int W, int H, YuvScratch& sc, uint8_t* out, cudaStream_t s ) {
+  const size_t Q = size_t( W ) * H, q4 = size_t( W / 2 ) * ( H / 2 );
+  sc.U.reserve( Q ), sc.V.reserve( Q ), sc.tU.reserve( Q / 2 + 1 ), sc.tV.reserve( Q / 2 + 1 );
+  kRgbToYuv444<<<divUp( Q, 256 ), 256, 0, s>>>( rgbPlanes, Q, out, sc.U, sc.V );
+  kChromaDownH<<<dim3( divUp( size_t( W / 2 ) * H, 256 ), 1, 2 ), 256, 0, s>>>( sc.U, sc.V, W, H, sc.tU, sc.tV );
+  kChromaDownV<<<dim3( divUp( q4, 256 ), 1, 2 ), 256, 0, s>>>( sc.tU, sc.tV, W / 2, H, out + Q, out + Q + q4 );
+  PCC_LAUNCH_CHECK();
+}
+
 }  // namespace pccb200

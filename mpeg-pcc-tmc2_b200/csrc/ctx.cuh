@@ -33,6 +33,7 @@ struct FrameState {
   CanvasImages               im;
   ReconScratch               rc;
   AttrImages                 attr;
+  YuvScratch                 yuv;
   Profiler                   prof;
   bool                       decodedSet = false;  // the caller replaced om/geo0/geo1 by decoded planes
   int                        status = 0;

@@ -608,6 +608,17 @@ size_t pccb200_gof_get( pccb200_gof* g, int f, int what, void* dst ) {
       case PCCB200_GOF_ATTR1_RAW: result = copyOut( dst, fs.attr.rawPlanes[1], 3 * Q, 2, s ); break;
       case PCCB200_GOF_ATTR0: result = copyOut( dst, fs.attr.planes[0], 3 * Q, 2, s ); break;
       case PCCB200_GOF_ATTR1: result = copyOut( dst, fs.attr.planes[1], 3 * Q, 2, s ); break;
+      case PCCB200_GOF_ATTR0_YUV420:
+      case PCCB200_GOF_ATTR1_YUV420: {
+        const int m = what == PCCB200_GOF_ATTR0_YUV420 ? 0 : 1;
+        result      = Q + 2 * ( ( g->W / 2 ) * ( g->H / 2 ) );
+        if ( dst ) {  // converted on request: the frame leaves the device with 1.5 bytes per pixel
+          fs.yuv.out[m].reserve( result );
+          rgbPlanesToYuv420( fs.attr.planes[m], int( g->W ), int( g->H ), fs.yuv, fs.yuv.out[m], s );
+          copyOut( dst, fs.yuv.out[m], result, 1, s );
+        }
+        break;
+      }
       default: break;
     }
     return 0;

@@ -152,6 +152,13 @@ FrameScratch* acquireFrameScratch( int device );             // blocks while all
 void          releaseFrameScratch( int device, FrameScratch* );
 int           setFrameScratchSets( int device, int count );  // upper bound of sets (>= 1); returns the previous bound
 
+// color.cu: RGB444 planes (uint16, 8-bit values) -> 8-bit YUV 4:2:0 (Y plane, then U, then V), W and H even
+struct YuvScratch {
+  DevBuf<float>   U, V, tU, tV;
+  DevBuf<uint8_t> out[2];
+};
+void rgbPlanesToYuv420( const uint16_t* rgbPlanes, int W, int H, YuvScratch& sc, uint8_t* out, cudaStream_t s );
+
 // util.cu
 void projectedAreas( const short4* pts, size_t n, int bits, uint32_t* faces, unsigned* counts, cudaStream_t s );
 void gatherU8( const uint8_t* src, const uint32_t* idx, size_t n, uint8_t* dst, cudaStream_t s );

@@ -869,6 +869,7 @@ struct OFrame {
   std::vector<uint8_t>  occupancy, omVideo, recRgb;
   std::vector<uint32_t> blockToPatch, pointToPixel, recPartition;
   std::vector<uint16_t> geo[2], recBoundary, attrRaw[2], attr[2];
+  std::vector<uint8_t>  attrYuv[2];  // 8-bit YUV 4:2:0 of the padded attribute frames (Y, U, V planes)
   std::vector<int16_t>  recXyz;
 };
 struct OGof {
@@ -1379,6 +1380,65 @@ void gpaRun( std::vector<OFrame>& frames, int occRes, size_t frameWidthIn, size_
   }
 }
 
+// ---- §8f-2: RGB444 -> YUV420 as PCCVideoEncoder::compress does it before the attribute video goes to the codec
+// (L/PccLibEncoder/source/PCCVideoEncoder.cpp:331-353: PCCInternalColorConverter "RGB444ToYUV420_8_4"; source
+//  L/PccLibColorConverter/source/PCCInternalColorConverter.cpp:407-424, 553-593, 642-666 and the inline filters of
+//  L/PccLibColorConverter/include/PCCInternalColorConverter.h:153-183). Filter 4 (DF_GS, the default of compress()):
+//  the taps are the reference's own constants, float( c * 512 ).
+const float kGsHor[15] = {float( -0.01716352771649 * 512 ), float( 0.0 ), float( +0.04066666714886 * 512 ), float( 0.0 ),
+                          float( -0.09154810319329 * 512 ), float( 0.0 ), float( 0.31577823859943 * 512 ), float( 0.50453345032298 * 512 ),
+                          float( 0.31577823859943 * 512 ), float( 0.0 ), float( -0.09154810319329 * 512 ), float( 0.0 ),
+                          float( 0.04066666714886 * 512 ), float( 0.0 ), float( -0.01716352771649 * 512 )};
+const float kGsVer[16] = {float( -0.00945406160902 * 512 ), float( -0.01539537217249 * 512 ), float( 0.02360533018213 * 512 ),
+                          float( 0.03519540819902 * 512 ), float( -0.05254456550808 * 512 ), float( -0.08189331229717 * 512 ),
+                          float( 0.14630826357715 * 512 ), float( 0.45417830962846 * 512 ), float( 0.45417830962846 * 512 ),
+                          float( 0.14630826357715 * 512 ), float( -0.08189331229717 * 512 ), float( -0.05254456550808 * 512 ),
+                          float( 0.03519540819902 * 512 ), float( 0.02360533018213 * 512 ), float( -0.01539537217249 * 512 ),
+                          float( -0.00945406160902 * 512 )};
+inline uint8_t quantise8( float v, bool chroma ) {  // floatYUVToYUV, nbyte 1
+  float r = std::round( float( 255. * double( v ) + ( chroma ? 128. : 0. ) ) );
+  r       = r < 0.f ? 0.f : r;
+  r       = r > 255.f ? 255.f : r;
+  return uint8_t( uint16_t( r ) );
+}
+void rgbToYuv420( const std::vector<uint16_t>& rgbPlanes, size_t W, size_t H, std::vector<uint8_t>& out ) {
+  const size_t       Q = W * H, w2 = W / 2, h2 = H / 2;
+  std::vector<float> U( Q ), V( Q );
+  out.assign( Q + 2 * w2 * h2, 0 );
+  for ( size_t i = 0; i < Q; ++i ) {
+    const float  r = float( rgbPlanes[i] ) / 255.f, g = float( rgbPlanes[Q + i] ) / 255.f, b = float( rgbPlanes[2 * Q + i] ) / 255.f;
+    const double y = 0.212600 * r + 0.715200 * g + 0.072200 * b, u = -0.114572 * r - 0.385428 * g + 0.500000 * b,
+                 v = 0.500000 * r - 0.454153 * g - 0.045847 * b;
+    out[i] = quantise8( float( y < 0.0 ? 0.0 : ( y > 1.0 ? 1.0 : y ) ), false );
+    U[i]   = float( u < -0.5 ? -0.5 : ( u > 0.5 ? 0.5 : u ) );
+    V[i]   = float( v < -0.5 ? -0.5 : ( v > 0.5 ? 0.5 : v ) );
+  }
+  const float scale = 1.0f / float( 1 << 9 );
+  auto        down  = [&]( const std::vector<float>& in, uint8_t* dst ) {
+    std::vector<float> tmp( w2 * H );
+    for ( size_t i = 0; i < H; ++i )
+      for ( size_t j = 0; j < w2; ++j ) {
+        double acc = 0;
+        for ( int t = 0; t < 15; ++t ) {
+          const long x = std::min<long>( std::max<long>( long( 2 * j ) + t - 7, 0 ), long( W ) - 1 );
+          acc += double( kGsHor[t] ) * double( in[i * W + size_t( x )] );
+        }
+        tmp[i * w2 + j] = float( ( acc + double( 0.f ) ) * double( scale ) );
+      }
+    for ( size_t i = 0; i < h2; ++i )
+      for ( size_t j = 0; j < w2; ++j ) {
+        double acc = 0;
+        for ( int t = 0; t < 16; ++t ) {
+          const long y = std::min<long>( std::max<long>( long( 2 * i ) + t - 7, 0 ), long( H ) - 1 );
+          acc += double( kGsVer[t] ) * double( tmp[size_t( y ) * w2 + j] );
+        }
+        dst[i * w2 + j] = quantise8( float( ( acc + double( 0.f ) ) * double( scale ) ), true );
+      }
+  };
+  down( U, out.data() + Q );
+  down( V, out.data() + Q + w2 * h2 );
+}
+
 // weighted mean used by the push-pull filter (PCCEncoder.cpp:6357-6369)
 inline int mean4w( int p1, int w1, int p2, int w2, int p3, int w3, int p4, int w4 ) {
   return ( p1 * w1 + p2 * w2 + p3 * w3 + p4 * w4 ) / ( w1 + w2 + w3 + w4 );
@@ -1771,6 +1831,7 @@ void* pcco_encode_gof_canvas( int nframes, const int16_t* const* xyz, const uint
       pushPull( T[map], occ );
       F.attr[map].resize( 3 * W * H );
       for ( int k = 0; k < 3; ++k ) std::copy( T[map].c[k].begin(), T[map].c[k].end(), F.attr[map].begin() + k * W * H );
+      rgbToYuv420( F.attr[map], W, H, F.attrYuv[map] );
     }
   }
   return G;
@@ -1802,6 +1863,8 @@ size_t pcco_gof_get( void* h, int f, int what, void* dst ) {
     case 12: put( R.attrRaw[1].data(), R.attrRaw[1].size() * 2 ); return R.attrRaw[1].size();
     case 13: put( R.attr[0].data(), R.attr[0].size() * 2 ); return R.attr[0].size();
     case 14: put( R.attr[1].data(), R.attr[1].size() * 2 ); return R.attr[1].size();
+    case 15: put( R.attrYuv[0].data(), R.attrYuv[0].size() ); return R.attrYuv[0].size();
+    case 16: put( R.attrYuv[1].data(), R.attrYuv[1].size() ); return R.attrYuv[1].size();
     default: return 0;
   }
 }

@@ -9,6 +9,7 @@
 // (built with -fno-access-control so the harness can call the reference's private stage methods)
 // The reference's PCCEncoder.cpp, unmodified, is part of this translation unit (see oracle/Makefile).
 #include "PCCEncoder.cpp"
+#include "PCCInternalColorConverter.h"
 #include "PCCCommon.h"
 #include "PCCHighLevelSyntax.h"
 #include "PCCBitstream.h"
@@ -324,6 +325,7 @@ struct RefFrame {
   std::vector<uint16_t> recBoundary;
   std::vector<uint8_t>  recRgb;
   std::vector<uint16_t> attrRaw[2], attr[2];
+  std::vector<uint8_t>  attrYuv[2];
 };
 struct RefGof {
   std::vector<RefFrame> frames;
@@ -518,6 +520,19 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
       G->seconds[6] = secs( t0 );
       for ( int f = 0; f < nframes; ++f )
         for ( int m = 0; m < 2; ++m ) planes( video.getFrame( 2 * f + m ), G->frames[f].attr[m] );
+      // what PCCVideoEncoder::compress does to this video before it reaches the codec (PCCVideoEncoder.cpp:326-353, internal
+      // colour converter, 8 bit, default down-sampling filter 4)
+      PCCVideoAttribute                   yuv = video;
+      PCCInternalColorConverter<uint16_t> converter;
+      converter.convert( "RGB444ToYUV420_8_4", yuv );
+      for ( int f = 0; f < nframes; ++f )
+        for ( int m = 0; m < 2; ++m ) {
+          auto& img = yuv.getFrame( 2 * f + m );
+          auto& out = G->frames[f].attrYuv[m];
+          out.clear();
+          for ( int c = 0; c < 3; ++c )
+            for ( auto v : img.getChannel( c ) ) out.push_back( uint8_t( v ) );
+        }
     }
     G->seconds[7] = secs( tAll );
   }
@@ -558,6 +573,8 @@ size_t ref_gof_get( void* h, int f, int what, void* dst ) {
     case 12: put( R.attrRaw[1].data(), R.attrRaw[1].size() * 2 ); return R.attrRaw[1].size();
     case 13: put( R.attr[0].data(), R.attr[0].size() * 2 ); return R.attr[0].size();
     case 14: put( R.attr[1].data(), R.attr[1].size() * 2 ); return R.attr[1].size();
+    case 15: put( R.attrYuv[0].data(), R.attrYuv[0].size() ); return R.attrYuv[0].size();
+    case 16: put( R.attrYuv[1].data(), R.attrYuv[1].size() ); return R.attrYuv[1].size();
     default: return 0;
   }
 }

@@ -416,8 +416,9 @@ class Product:
 # ---------------------------------------------------------------------------------------- GOF-level products
 GOF_OCCUPANCY, GOF_OM_VIDEO, GOF_BLOCK_TO_PATCH, GOF_GEO0, GOF_GEO1, GOF_REC_XYZ, GOF_POINT_TO_PIXEL = 1, 2, 3, 4, 5, 6, 7
 GOF_REC_PARTITION, GOF_REC_BOUNDARY, GOF_REC_RGB, GOF_ATTR0_RAW, GOF_ATTR1_RAW, GOF_ATTR0, GOF_ATTR1 = 8, 9, 10, 11, 12, 13, 14
+GOF_ATTR0_YUV420, GOF_ATTR1_YUV420 = 15, 16
 GOF_DTYPES = {1: np.uint8, 2: np.uint8, 3: np.uint32, 4: np.uint16, 5: np.uint16, 6: np.int16, 7: np.uint32, 8: np.uint32,
-              9: np.uint16, 10: np.uint8, 11: np.uint16, 12: np.uint16, 13: np.uint16, 14: np.uint16}
+              9: np.uint16, 10: np.uint8, 11: np.uint16, 12: np.uint16, 13: np.uint16, 14: np.uint16, 15: np.uint8, 16: np.uint8}
 
 
 class GofFrame:
@@ -528,7 +529,8 @@ def _oracle_encode_gof(self, frames, params, occupancy_precision=4, stop_after=0
 
 Oracle.encode_gof = _oracle_encode_gof
 GOF_NAMES = {1: "occupancy", 2: "om_video", 3: "block_to_patch", 4: "geo0", 5: "geo1", 6: "rec_xyz", 7: "point_to_pixel", 8: "rec_partition",
-             9: "rec_boundary", 10: "rec_rgb", 11: "attr0_raw", 12: "attr1_raw", 13: "attr0", 14: "attr1"}
+             9: "rec_boundary", 10: "rec_rgb", 11: "attr0_raw", 12: "attr1_raw", 13: "attr0", 14: "attr1", 15: "attr0_yuv420",
+             16: "attr1_yuv420"}
 
 
 def compare_gof(got, want, attr_tol=0):
@@ -553,7 +555,7 @@ def compare_gof(got, want, attr_tol=0):
             x, y = a.data[what], b.data[what]
             if x.shape != y.shape:
                 bad.append("frame %d %s size %d != %d" % (f, name, x.size, y.size))
-            elif what in (10, 11, 12, 13, 14) and attr_tol > 0:
+            elif what in (10, 11, 12, 13, 14, 15, 16) and attr_tol > 0:
                 d = np.abs(x.astype(np.int32) - y.astype(np.int32))
                 if d.size and d.max() > attr_tol:
                     bad.append("frame %d %s max abs diff %d (> %d) at %d samples" % (f, name, d.max(), attr_tol, int((d > attr_tol).sum())))

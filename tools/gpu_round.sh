@@ -1,8 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 500 > gpurun_out/clocks.csv &
-SMI=$!
-( time timeout 900 python bench.py ) > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "default rc=$?"; cut -c1-300 gpurun_out/bench_default.json; tail -4 gpurun_out/bench_default.err
-kill $SMI
-( time timeout 900 python bench.py --impl reference ) > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_reference.json; tail -4 gpurun_out/bench_reference.err
+( timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
+( time timeout 900 python bench.py --no-cpu-baseline ) > gpurun_out/bench_yuv.json 2> gpurun_out/bench_yuv.err; echo "rc=$?"; python - <<P
+import json
+try:
+    d=json.load(open('gpurun_out/bench_yuv.json')); print(round(d['value'],2), d['e2e'], d['gpu_mem_used_gb'], d['host_ms_per_gof'])
+except Exception as e: print('ERR', e)
+P
+tail -4 gpurun_out/bench_yuv.err
