@@ -238,7 +238,7 @@ __global__ void kRecount( VoxState st, const uint32_t* __restrict__ voxStart, co
                           const uint32_t* __restrict__ idsSorted, const uint8_t* __restrict__ partition, int V, int initialise,
                           uint32_t* __restrict__ list, unsigned* __restrict__ ctl ) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( v < 3 ) ctl[v] = 0;
+  if ( v < 4 ) ctl[v] = 0;
   if ( v >= V ) return;
   list[v] = kNoEntry;
   const uint32_t s = voxStart[v], c = voxCount[v];
@@ -274,12 +274,18 @@ __global__ void kRecount( VoxState st, const uint32_t* __restrict__ voxStart, co
 }
 
 // initial work list of a sweep: voxels that are edge voxels at sweep start
-__global__ void kInitialActive( VoxState st, int V, uint32_t* __restrict__ list, unsigned* __restrict__ count ) {
+__global__ void kInitialActive( VoxState st, int V, uint32_t* __restrict__ list, unsigned* __restrict__ count, int staticPhase ) {
   const int  v   = blockIdx.x * blockDim.x + threadIdx.x;
   const bool on  = v < V && st.edge[v] != NO_EDGE;
   const unsigned m = __ballot_sync( 0xffffffffu, on );
   unsigned   base = 0;
-  if ( ( threadIdx.x & 31 ) == 0 && m ) base = atomicAdd( count, __popc( m ) );
+  if ( ( threadIdx.x & 31 ) == 0 && m ) {
+    base = atomicAdd( count, __popc( m ) );
+    if ( staticPhase ) {  // count[3] = length of the initial list, count[1] = first ticket of the entries appended later
+      atomicAdd( count + 3, __popc( m ) );
+      atomicAdd( count + 1, __popc( m ) );
+    }
+  }
   base = __shfl_sync( 0xffffffffu, base, 0 );
   if ( on ) {
     st.active[v]                                              = 1;
@@ -297,14 +303,31 @@ __device__ __forceinline__ unsigned ldVolatile( const unsigned* p ) { return *re
 __global__ void __launch_bounds__( 128 )
     kSmoothAndMark( VoxState st, uint32_t* __restrict__ list, unsigned* __restrict__ ctl, const uint32_t* __restrict__ adjOff,
                     const uint32_t* __restrict__ adjLen, const uint32_t* __restrict__ adjData, const uint32_t* __restrict__ nearData,
-                    const uint8_t* __restrict__ nearLen, uint16_t* __restrict__ smooth, unsigned maxSleepNs ) {
+                    const uint8_t* __restrict__ nearLen, uint16_t* __restrict__ smooth, unsigned maxSleepNs, int staticPhase ) {
   const int lane = threadIdx.x & 31;
+  // Static phase (optional): the entries kInitialActive wrote (complete before this launch) are dealt out by warp index - no
+  // ticket and no "finished" atomic per voxel on two words every warp of the grid hammers; tickets are only drawn for the
+  // entries appended during the sweep.
+  unsigned       nextStatic = staticPhase ? ( blockIdx.x * blockDim.x + threadIdx.x ) / 32 : 0u;
+  const unsigned nWarps = gridDim.x * ( blockDim.x / 32 ), initial = staticPhase ? ctl[3] : 0u;
+  unsigned       staticDone = 0;
   for ( ;; ) {
     unsigned w = 0;
-    if ( lane == 0 ) w = atomicAdd( &ctl[1], 1u );
-    w          = __shfl_sync( 0xffffffffu, w, 0 );
     uint32_t v = kNoEntry;
-    if ( lane == 0 ) {
+    const bool fromStatic = nextStatic < initial;
+    if ( fromStatic ) {
+      v = list[nextStatic];
+      nextStatic += nWarps;
+    } else {
+      if ( staticDone ) {  // this warp's share of the initial list is finished: publish it once
+        __threadfence();
+        if ( lane == 0 ) atomicAdd( &ctl[2], staticDone );
+        staticDone = 0;
+      }
+      if ( lane == 0 ) w = atomicAdd( &ctl[1], 1u );
+      w = __shfl_sync( 0xffffffffu, w, 0 );
+    }
+    if ( !fromStatic && lane == 0 ) {
       unsigned nap = 128;  // (the waiters poll L2: back off, the other frames' kernels share it)
       for ( ;; ) {
         const unsigned c0 = ldVolatile( &ctl[0] );
@@ -351,7 +374,10 @@ __global__ void __launch_bounds__( 128 )
     }
     __threadfence();  // the entries appended above are reserved (and written) before this one counts as finished
     __syncwarp();
-    if ( lane == 0 ) atomicAdd( &ctl[2], 1u );
+    if ( fromStatic )
+      ++staticDone;
+    else if ( lane == 0 )
+      atomicAdd( &ctl[2], 1u );
   }
 }
 
@@ -521,13 +547,17 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
     return e && atoi( e ) > 0 ? atoi( e ) : 4;
   }();
   const int sweepCtas  = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * ctasPerSm ) );
+  static const int staticPhase = [] {  // (experimental, off by default: see kSmoothAndMark)
+    const char* e = getenv( "PCCB200_SWEEP_STATIC" );
+    return e && e[0] == '1' ? 1 : 0;
+  }();
   static const unsigned maxSleepNs = [] {
     const char* e = getenv( "PCCB200_SWEEP_MAX_SLEEP_NS" );
     return unsigned( e && atoi( e ) > 0 ? atoi( e ) : 2048 );
   }();
   for ( int it = 0; it < iterations; ++it ) {
-    kInitialActive<<<divUp( V, 256 ), 256, 0, s>>>( st, V, sc.list, ctl );
-    kSmoothAndMark<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.smooth, maxSleepNs );
+    kInitialActive<<<divUp( V, 256 ), 256, 0, s>>>( st, V, sc.list, ctl, staticPhase );
+    kSmoothAndMark<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.smooth, maxSleepNs, staticPhase );
     kRelabel<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.smooth, sc.weight, sc.voxStart, sc.voxCount, sc.idsSorted, normals, partition );
     kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 0, sc.list, ctl );
     PCC_LAUNCH_CHECK();

@@ -32,6 +32,11 @@ def gof(name):
         return [synth.sheet_stack(11, f, spacing=6, gap=28) for f in range(4)]
     if name == "single":
         return [fig(0)]
+    if name == "empty_mid":  # an empty frame is legal (PCCEncoder.cpp:3688, 4772-4774): it ends the sub-context and starts its own
+        empty = (np.zeros((0, 3), np.int16), np.zeros((0, 3), np.uint8))
+        return [fig(0, 0.12), fig(1, 0.12), empty, fig(2, 0.12), fig(3, 0.12)]
+    if name == "tiny":       # a 40-point frame (one patch) between two ordinary ones
+        return [fig(0, 0.12), synth.random_cloud(40, 8, 1), fig(1, 0.12)]
     raise KeyError(name)
 
 
@@ -41,7 +46,7 @@ def ra_params(weight, iterations=3):
     return prm
 
 
-@pytest.mark.parametrize("name", ["mixed", "jumpy", "stack", "single"])
+@pytest.mark.parametrize("name", ["mixed", "jumpy", "stack", "single", "empty_mid", "tiny"])
 def test_oracle_ra_packing_vs_reference(name, oracle, reference):
     frames = gof(name)
     prm = ra_params(reference.weight_normal(frames[0][0], 11))
@@ -72,7 +77,7 @@ def shim():
     return lib
 
 
-@pytest.mark.parametrize("name", ["mixed", "jumpy", "stack", "single"])
+@pytest.mark.parametrize("name", ["mixed", "jumpy", "stack", "single", "empty_mid", "tiny"])
 def test_product_ra_host_logic_vs_oracle(name, oracle, shim):
     frames = gof(name)
     prm = ra_params(oracle.weight_normal(frames[0][0], 11), iterations=2)
@@ -105,7 +110,7 @@ def test_product_ra_host_logic_vs_oracle(name, oracle, shim):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["mixed", "jumpy", "stack", "single"])
+@pytest.mark.parametrize("name", ["mixed", "jumpy", "stack", "single", "empty_mid", "tiny"])
 def test_gpu_ra_gof_vs_oracle(name, oracle, product):
     frames = gof(name)
     w = product.weight_normal(frames[0][0], 11)
