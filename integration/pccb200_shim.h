@@ -1,0 +1,40 @@
+// pccb200_shim.h — the reference-side binding of libpccb200.so: what a maintainer adds to PccLibEncoder so that
+// PCCEncoder::encode (PccLibEncoder/source/PCCEncoder.cpp:71-424) runs its hot path on the GPU and everything else
+// (PccAppEncoder, bitstream writer, video-codec wrappers, post-processing, metrics) stays as it is.
+//
+// It is written against the reference's own headers and types (C++14) and only calls the C ABI of include/pccb200.h.
+// The three stage functions are drop-in bodies for the calls PCCEncoder::encode makes:
+//   stageA  : generateSegments (:103) + placeSegments (:110) + generateOccupancyMap (:133) + generateOccupancyMapVideo (:139)
+//             + generateBlockToPatchFromOccupancyMapVideo (:168) + generateGeometryVideo (:172)
+//             (params_.initializeContext( context ), :107, stays between "segments" and "placement": it is called from here)
+//   stageB1 : the generatePointCloud loop (:319-334) + generateAttributeVideo (:341)
+//   stageB2 : the attribute padding loop (:344-424)
+// In-tree this file is compiled and linked by oracle/Makefile (target `shim`, against the reference sources where they lie)
+// and exercised by tests/test_shim.py: on a GPU box the reference's own data structures, filled through this shim, must be
+// identical to what the unmodified reference stages leave in them.
+#pragma once
+#include <vector>
+
+#include "PCCContext.h"
+#include "PCCEncoderParameters.h"
+#include "PCCGroupOfFrames.h"
+#include "pccb200.h"
+
+namespace pccb200shim {
+
+struct Session {  // one per PCCEncoder object
+  pccb200_ctx* ctx = nullptr;
+  pccb200_gof* gof = nullptr;
+  ~Session();
+};
+
+// the fields PCCEncoder::generateSegments copies into PCCPatchSegmenter3Parameters (PCCEncoder.cpp:4672-4727), plus the packing mode
+pccb200_seg_params toSegParams( const pcc::PCCEncoderParameters& p );
+
+// each returns 0 or a negative pccb200_status (the caller keeps the reference's convention: print + exit)
+int stageA( Session& s, pcc::PCCEncoderParameters& params, const pcc::PCCGroupOfFrames& sources, pcc::PCCContext& context );
+int stageB1( Session& s, const pcc::PCCEncoderParameters& params, pcc::PCCContext& context, pcc::PCCGroupOfFrames& reconstructs,
+             std::vector<std::vector<uint32_t>>& partitions );
+int stageB2( Session& s, pcc::PCCContext& context );
+
+}  // namespace pccb200shim

@@ -378,6 +378,21 @@ void setCtcParams( PCCEncoderParameters& ep, const pccb200_seg_params& p, int oc
   ep.compressedStreamPath_                = "/tmp/pccb200_ref_harness.bin";
 }
 
+}  // namespace
+
+// Optional replacement of the hot-path stages by an external implementation (oracle/shim_harness.cpp registers the reference-side
+// shim of libpccb200 here): everything else of ref_encode_gof - set-up, the order of the steps, the extraction of the products from
+// the reference's own data structures - is shared, so the two runs differ in nothing but who filled those structures.
+struct RefHotPathHooks {
+  int ( *stageA )( PCCEncoder& enc, PCCGroupOfFrames& sources, PCCContext& context );
+  int ( *stageB1 )( PCCEncoder& enc, PCCContext& context, PCCGroupOfFrames& reconstructs, std::vector<std::vector<uint32_t>>& partitions );
+  int ( *stageB2 )( PCCEncoder& enc, PCCContext& context );
+};
+static const RefHotPathHooks* gHooks = nullptr;
+extern "C" void ref_set_hot_path_hooks( const RefHotPathHooks* hooks ) { gHooks = hooks; }
+
+namespace {
+
 template <typename T>
 void planes( const PCCImage<T, 3>& img, std::vector<uint16_t>& out ) {
   const size_t n = img.getWidth() * img.getHeight();
@@ -435,13 +450,24 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
       fc.setLog2PatchQuantizerSizeX( enc.params_.log2QuantizerSizeX_ );
       fc.setLog2PatchQuantizerSizeY( enc.params_.log2QuantizerSizeY_ );
     }
+    const RefHotPathHooks* hooks = gHooks;
+    int                    hookError = 0;
     auto t0 = clk::now();
-    enc.generateSegments( sources, context );  // :103
-    G->seconds[0] = secs( t0 );
-    enc.params_.initializeContext( context );   // :107
-    t0 = clk::now();
-    enc.placeSegments( sources, context );  // :110
-    G->seconds[1] = secs( t0 );
+    if ( hooks ) {
+      hookError = hooks->stageA( enc, sources, context );  // :103-172 through the external implementation
+    } else {
+      enc.generateSegments( sources, context );  // :103
+      G->seconds[0] = secs( t0 );
+      enc.params_.initializeContext( context );   // :107
+      t0 = clk::now();
+      enc.placeSegments( sources, context );  // :110
+      G->seconds[1] = secs( t0 );
+    }
+    if ( hookError ) {
+      G->frames.clear();
+      nframes = 0;
+      stopAfter = 1;
+    }
     for ( int f = 0; f < nframes; ++f ) {
       auto& tile             = context[f].getTile( 0 );
       G->frames[f].patches.patches = tile.getPatches();
@@ -450,9 +476,11 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
     }
     if ( stopAfter != 1 ) {
       t0 = clk::now();
-      enc.generateOccupancyMap( context, true );         // :133
-      enc.generateOccupancyMapVideo( sources, context );  // :139  (compress skipped: lossless)
-      enc.generateBlockToPatchFromOccupancyMapVideo( context, enc.params_.occupancyResolution_, enc.params_.occupancyPrecision_ );  // :168
+      if ( !hooks ) {
+        enc.generateOccupancyMap( context, true );         // :133
+        enc.generateOccupancyMapVideo( sources, context );  // :139  (compress skipped: lossless)
+        enc.generateBlockToPatchFromOccupancyMapVideo( context, enc.params_.occupancyResolution_, enc.params_.occupancyPrecision_ );  // :168
+      }
       G->seconds[2] = secs( t0 );
       for ( int f = 0; f < nframes; ++f ) {
         auto& R   = G->frames[f];
@@ -464,7 +492,7 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
         R.blockToPatch.assign( b2p.begin(), b2p.end() );
       }
       t0 = clk::now();
-      enc.generateGeometryVideo( sources, context );  // :172
+      if ( !hooks ) enc.generateGeometryVideo( sources, context );  // :172
       G->seconds[3] = secs( t0 );
       for ( int f = 0; f < nframes; ++f )
         for ( int m = 0; m < 2; ++m ) {
@@ -478,10 +506,14 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
       enc.setGeneratePointCloudParameters( gpc, context );  // :315
       context.allocOneLayerData();
       std::vector<std::vector<uint32_t>> partitions( context.size() );
-      for ( size_t f = 0; f < context.size(); f++ ) {
-        PCCPointSet3 rec;
-        enc.generatePointCloud( rec, context, f, 0, gpc, partitions[f], false );  // :328
-        reconstructs[f].appendPointSet( rec );
+      if ( hooks ) {
+        hooks->stageB1( enc, context, reconstructs, partitions );  // :319-341 through the external implementation
+      } else {
+        for ( size_t f = 0; f < context.size(); f++ ) {
+          PCCPointSet3 rec;
+          enc.generatePointCloud( rec, context, f, 0, gpc, partitions[f], false );  // :328
+          reconstructs[f].appendPointSet( rec );
+        }
       }
       G->seconds[4] = secs( t0 );
       for ( int f = 0; f < nframes; ++f ) {
@@ -502,7 +534,7 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
     }
     if ( stopAfter == 0 ) {
       t0 = clk::now();
-      enc.generateAttributeVideo( sources, reconstructs, context, enc.params_ );  // :341
+      if ( !hooks ) enc.generateAttributeVideo( sources, reconstructs, context, enc.params_ );  // :341
       G->seconds[5] = secs( t0 );
       auto& video = context.getVideoAttributesMultiple()[0];
       for ( int f = 0; f < nframes; ++f ) {
@@ -515,8 +547,12 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
           for ( int d = 0; d < 3; ++d ) R.recRgb[3 * i + d] = rec.getColor( i )[d];
       }
       t0 = clk::now();
-      for ( int f = 0; f < nframes; ++f )
-        for ( int m = 0; m < 2; ++m ) enc.dilateSmoothedPushPull( frames[f].getTitleFrameContext(), video.getFrame( 2 * f + m ) );  // :367
+      if ( hooks ) {
+        hooks->stageB2( enc, context );  // :344-424 through the external implementation
+      } else {
+        for ( int f = 0; f < nframes; ++f )
+          for ( int m = 0; m < 2; ++m ) enc.dilateSmoothedPushPull( frames[f].getTitleFrameContext(), video.getFrame( 2 * f + m ) );  // :367
+      }
       G->seconds[6] = secs( t0 );
       for ( int f = 0; f < nframes; ++f )
         for ( int m = 0; m < 2; ++m ) planes( video.getFrame( 2 * f + m ), G->frames[f].attr[m] );

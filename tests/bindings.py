@@ -486,6 +486,54 @@ def _ref_encode_gof(self, frames, params, occupancy_precision=4, stop_after=0):
 
 Reference.encode_gof = _ref_encode_gof
 
+SHIM_SO = os.path.join(os.path.dirname(REF_SO), "libtmc2shim.so")
+
+
+class Shim:
+    """the reference's encoder harness with its hot path replaced by the reference-side shim of libpccb200
+    (integration/pccb200_shim.cpp; oracle/Makefile target `shim`). Products are read from the reference's own data structures."""
+
+    def __init__(self, path=SHIM_SO):
+        self.ref = Reference()
+        self.lib = C.CDLL(path)
+        self.lib.shim_encode_gof.restype = C.c_void_p
+        self.lib.shim_encode_gof.argtypes = [C.c_int, C.POINTER(c_i16p), C.POINTER(c_u8p), C.POINTER(C.c_size_t), C.POINTER(SegParams), C.c_int,
+                                             C.c_int, C.POINTER(C.c_int)]
+
+    @staticmethod
+    def available():
+        return os.path.exists(SHIM_SO) and os.path.exists(REF_SO) and os.path.exists(PRODUCT_SO)
+
+    def encode_gof(self, frames, params, occupancy_precision=4, stop_after=0):
+        """returns (list of GofFrame, status code of the last pccb200 call; frames are empty when the hot path failed)"""
+        L = self.ref.lib
+        L.ref_gof_free.argtypes = [C.c_void_p]
+        L.ref_gof_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.ref_gof_patches.restype = C.c_void_p
+        L.ref_gof_patches.argtypes = [C.c_void_p, C.c_int]
+        L.ref_gof_get.restype = C.c_size_t
+        L.ref_gof_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        n, xs, cs, xp, cp, ns = _frames_args(frames)
+        code = C.c_int(0)
+        h = self.lib.shim_encode_gof(n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after, C.byref(code))
+        out = []
+        if code.value == 0:
+            for f in range(n):
+                g = GofFrame()
+                w, hh, r = C.c_size_t(), C.c_size_t(), C.c_size_t()
+                L.ref_gof_dims(h, f, C.byref(w), C.byref(hh), C.byref(r))
+                g.width, g.height = w.value, hh.value
+                g.patches = _collect_patches_borrowed(L, "ref_", L.ref_gof_patches(h, f))
+                for what, dt in GOF_DTYPES.items():
+                    cnt = L.ref_gof_get(h, f, what, None)
+                    a = np.zeros(cnt, dt)
+                    if cnt:
+                        L.ref_gof_get(h, f, what, a.ctypes.data_as(C.c_void_p))
+                    g.data[what] = a
+                out.append(g)
+        L.ref_gof_free(h)
+        return out, code.value
+
 
 def _generic_encode_gof(lib, prefix, frames, params, occupancy_precision=4, stop_after=0, canvas=None):
     g = lambda name: getattr(lib, prefix + name)
