@@ -96,6 +96,13 @@ const char* pccb200_version( void );
  * (default 24, or the environment variable PCCB200_SCRATCH_SETS). Returns the previous bound, or a negative pccb200_status. */
 int         pccb200_set_scratch_sets( int device, int count );
 
+/* Input side: PCCPointSet3::read (PccLibCommon/source/PCCPointSet.cpp:464-757) for what the hot path consumes - positions and
+ * colours of one .ply frame (ascii or binary, any of the reference's property types for x/y/z, uchar red/green/blue, other
+ * properties skipped), converted exactly as the reference's assignments convert them, written straight into caller buffers
+ * (pin them: they are what pccb200_encode_gof uploads). Host code, no device needed. Call with xyz == NULL to get the point
+ * count of the header in *n; capacity is in points; *has_colours (may be NULL) tells whether rgb was filled. */
+int pccb200_ply_read( const char* path, int16_t* xyz, uint8_t* rgb, size_t capacity, size_t* n, int* has_colours );
+
 /* Per-stage device timing (CUDA events on the launching stream). While enabled, every entry point appends one
  * (name, milliseconds) record per stage and frame; read returns and clears them. names: capacity x 32 chars; start_ms
  * (may be NULL) = start of the span relative to the beginning of the GOF call (-1 for the single-frame entry points). */

@@ -201,6 +201,23 @@ void ref_normals( const int16_t* xyz, size_t n, int k, int orientation, double* 
 }
 
 // ---- PCCEncoder::calculateWeightNormal (PccLibEncoder/source/PCCEncoder.cpp:3569-3626) ----------------
+// PCCPointSet3::read (PCCPointSet.cpp:464-757): positions and colours of a .ply file as the reference loads them
+int ref_read_ply( const char* path, int16_t* xyz, uint8_t* rgb, size_t capacity, size_t* n, int* hasColours ) {
+  Quiet        quiet;
+  PCCPointSet3 ps;
+  if ( !ps.read( path ) ) return -1;
+  *n          = ps.getPointCount();
+  *hasColours = ps.hasColors() ? 1 : 0;
+  if ( !xyz ) return 0;
+  if ( capacity < *n ) return -5;
+  for ( size_t i = 0; i < *n; ++i ) {
+    for ( int d = 0; d < 3; ++d ) xyz[3 * i + d] = ps[i][d];
+    if ( rgb && ps.hasColors() )
+      for ( int d = 0; d < 3; ++d ) rgb[3 * i + d] = ps.getColor( i )[d];
+  }
+  return 0;
+}
+
 void ref_weight_normal( const int16_t* xyz, size_t n, int bits, double minW, double w[3] ) {
   Quiet        quiet;
   PCCPointSet3 cloud;
