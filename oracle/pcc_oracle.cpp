@@ -1869,4 +1869,103 @@ size_t pcco_gof_get( void* h, int f, int what, void* dst ) {
   }
 }
 
+// ---- §8f-1 (first stage of the post-reconstruction chain): grid-based geometry smoothing, PCCCodec::smoothPointCloudPostprocess
+// with gridSmoothing (L/PccLibCommon/source/PCCCodec.cpp:54-150), addGridCentroid (:982-1000), gridFiltering (:1002-1065),
+// smoothPointCloudGrid (:1067-1106). In: the reconstructed cloud as generatePointCloud leaves it (positions, boundary point
+// types, patch index per point). Out: boundary points whose tri-linearly weighted neighbourhood centroid lies far enough away
+// move onto it and get boundary type 3.
+void pcco_smooth_geometry( int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int gridSize, double threshold ) {
+  if ( n == 0 ) return;
+  int maxSize = std::max( std::max( xyz[0], xyz[1] ), xyz[2] );
+  for ( size_t i = 0; i < 3 * n; ++i ) maxSize = std::max( maxSize, int( xyz[i] ) );
+  const int w = ( maxSize + gridSize - 1 ) / gridSize, disth = std::max( gridSize / 2, 1 ), th = gridSize * w, half = gridSize / 2;
+  auto      nearBorder = [&]( const int16_t* p ) {
+    return p[0] < disth || p[1] < disth || p[2] < disth || th <= p[0] + disth || th <= p[1] + disth || th <= p[2] + disth;
+  };
+  // cells around boundary points, numbered by first appearance
+  std::vector<int> cellIndex( size_t( w ) * w * w, -1 );
+  int              cells = 0;
+  for ( size_t i = 0; i < n; ++i ) {
+    const int16_t* p = xyz + 3 * i;
+    if ( boundary[i] != 1 || nearBorder( p ) ) continue;
+    int q[3];
+    for ( int k = 0; k < 3; ++k ) q[k] = p[k] / gridSize + ( p[k] % gridSize < half ? -1 : 0 );
+    for ( int ix = 0; ix < 2; ++ix )
+      for ( int iy = 0; iy < 2; ++iy )
+        for ( int iz = 0; iz < 2; ++iz ) {
+          int& c = cellIndex[size_t( q[0] + ix ) + size_t( q[1] + iy ) * w + size_t( q[2] + iz ) * w * w];
+          if ( c == -1 ) c = cells++;
+        }
+  }
+  // per cell: float centroid of all points in it (uint16 count, as the reference), first patch, "holds several patches" flag
+  std::vector<uint16_t> count( cells, 0 );
+  std::vector<float>    center( 3 * size_t( cells ), 0.f );
+  std::vector<uint32_t> firstPatch( cells, 0 );
+  std::vector<uint8_t>  mixed( cells, 0 );
+  for ( size_t i = 0; i < n; ++i ) {
+    const int16_t* p = xyz + 3 * i;
+    if ( nearBorder( p ) ) continue;
+    const int c = cellIndex[size_t( p[0] / gridSize ) + size_t( p[1] / gridSize ) * w + size_t( p[2] / gridSize ) * w * w];
+    if ( c == -1 ) continue;
+    const uint32_t patch = partition[i] + 1;
+    if ( count[c] == 0 ) {
+      firstPatch[c] = patch, mixed[c] = 0;
+      center[3 * c] = center[3 * c + 1] = center[3 * c + 2] = 0.f;
+    } else if ( !mixed[c] && firstPatch[c] != patch ) {
+      mixed[c] = 1;
+    }
+    for ( int k = 0; k < 3; ++k ) center[3 * c + k] += float( p[k] );
+    ++count[c];
+  }
+  for ( int c = 0; c < cells; ++c )
+    if ( count[c] )
+      for ( int k = 0; k < 3; ++k ) center[3 * c + k] /= float( count[c] );
+  // per boundary point (independent of one another: the grid is frozen)
+  const int g2 = gridSize * 2, w3 = w * w * w;
+  for ( size_t i = 0; i < n; ++i ) {
+    int16_t* p = xyz + 3 * i;
+    if ( nearBorder( p ) || boundary[i] != 1 ) continue;
+    int S[3], idx[2][2][2];
+    for ( int k = 0; k < 3; ++k ) S[k] = p[k] / gridSize + ( ( p[k] - ( p[k] / gridSize ) * gridSize ) < half ? -1 : 0 );
+    bool other = false;
+    for ( int dz = 0; dz < 2; ++dz )
+      for ( int dy = 0; dy < 2; ++dy )
+        for ( int dx = 0; dx < 2; ++dx ) {
+          const int t     = ( S[0] + dx ) + ( S[1] + dy ) * w + ( S[2] + dz ) * w * w;
+          idx[dz][dy][dx] = t;
+          const int c     = cellIndex[t];
+          if ( mixed[c] && count[c] != 0 ) other = true;
+        }
+    if ( !other ) continue;
+    const double cur[3] = {double( p[0] ), double( p[1] ), double( p[2] )};
+    int          W[3], Q[3];
+    for ( int k = 0; k < 3; ++k ) W[k] = ( p[k] - S[k] * gridSize - half ) * 2 + 1, Q[k] = g2 - W[k];
+    double sum[3] = {0.0, 0.0, 0.0};
+    int    cnt    = 0;
+    for ( int dz = 0; dz < 2; ++dz )
+      for ( int dy = 0; dy < 2; ++dy )
+        for ( int dx = 0; dx < 2; ++dx ) {
+          const int c = cellIndex[idx[dz][dy][dx]];
+          double    v[3] = {cur[0], cur[1], cur[2]};
+          if ( ( ( dx == 0 && dy == 0 && dz == 0 ) || idx[dz][dy][dx] < w3 ) && count[c] > 0 )
+            for ( int k = 0; k < 3; ++k ) v[k] = double( center[3 * c + k] );
+          const int wgt = ( dx ? W[0] : Q[0] ) * ( dy ? W[1] : Q[1] ) * ( dz ? W[2] : Q[2] );
+          for ( int k = 0; k < 3; ++k ) {
+            v[k] *= double( wgt );
+            sum[k] += v[k];
+          }
+          cnt += wgt * count[c];
+        }
+    for ( int k = 0; k < 3; ++k ) sum[k] /= double( g2 * g2 * g2 );
+    cnt /= g2 * g2 * g2;
+    double centroid[3], d[3];
+    for ( int k = 0; k < 3; ++k ) centroid[k] = sum[k] * double( cnt ), d[k] = cur[k] * double( cnt ) - centroid[k];
+    const double dist2 = ( d[0] * d[0] + d[1] * d[1] + d[2] * d[2] ) / double( cnt ) + 0.5;
+    if ( dist2 >= double( std::max( int( threshold ), cnt ) * 2 ) ) {
+      for ( int k = 0; k < 3; ++k ) p[k] = int16_t( double( int64_t( centroid[k] / double( cnt ) + 0.5 ) ) );
+      boundary[i] = 3;
+    }
+  }
+}
+
 }  // extern "C"

@@ -73,6 +73,9 @@ void   pcco_gof_dims( void* h, int f, size_t* w, size_t* hgt, size_t* rec_points
 void*  pcco_gof_patches( void* h, int f ); /* borrowed patch list for pcco_patches_* */
 size_t pcco_gof_get( void* h, int f, int what, void* dst );
 
+/* ---- §8f-1, first stage: grid-based geometry smoothing of the reconstructed cloud (PCCCodec.cpp:54-150, 982-1106); in place */
+void   pcco_smooth_geometry( int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int grid_size, double threshold );
+
 #ifdef __cplusplus
 }
 #endif

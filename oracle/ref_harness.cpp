@@ -218,6 +218,27 @@ int ref_read_ply( const char* path, int16_t* xyz, uint8_t* rgb, size_t capacity,
   return 0;
 }
 
+// PCCCodec::smoothPointCloudPostprocess, grid smoothing (PCCCodec.cpp:54-150), in place on positions / boundary point types
+void ref_smooth_geometry( int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int gridSize, double threshold ) {
+  Quiet        quiet;
+  PCCPointSet3 rec;
+  rec.resize( n );
+  for ( size_t i = 0; i < n; ++i ) {
+    rec[i] = PCCPoint3D( xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2] );
+    rec.setBoundaryPointType( i, boundary[i] );
+  }
+  std::vector<uint32_t>        part( partition, partition + n );
+  GeneratePointCloudParameters gp;
+  gp.flagGeometrySmoothing_ = true, gp.gridSmoothing_ = true, gp.gridSize_ = size_t( gridSize ), gp.thresholdSmoothing_ = threshold;
+  gp.pbfEnableFlag_         = false;
+  PCCEncoder enc;
+  enc.smoothPointCloudPostprocess( rec, COLOR_TRANSFORM_NONE, gp, part );
+  for ( size_t i = 0; i < n; ++i ) {
+    for ( int d = 0; d < 3; ++d ) xyz[3 * i + d] = rec[i][d];
+    boundary[i] = rec.getBoundaryPointType( i );
+  }
+}
+
 void ref_weight_normal( const int16_t* xyz, size_t n, int bits, double minW, double w[3] ) {
   Quiet        quiet;
   PCCPointSet3 cloud;
