@@ -105,3 +105,20 @@ def test_product_refuses_to_run_without_a_gpu():
     lib = C.CDLL(bindings.PRODUCT_SO)
     ctx = C.c_void_p()
     assert lib.pccb200_create(0, C.byref(ctx)) == -1  # PCCB200_ERR_NO_DEVICE: there is no CPU fallback
+
+
+@pytest.mark.parametrize("name,prec,overrides", [
+    ("patch_splitting", 4, dict(max_patch_size=64)),          # the a9 clamp (PCCPatchSegmenter.cpp:929-957) on clouds smaller than 1024
+    ("precision1_thin", 1, dict(surface_thickness=2)),
+    ("levels_and_cc", 4, dict(min_level=32, min_point_count_per_cc=8)),
+    ("refine_knobs", 4, dict(lambda_refine=1.0, search_radius_refine=96)),
+    ("no_orientation_no_splitting", 4, dict(normal_orientation=0, enable_patch_splitting=0)),
+])
+def test_oracle_gof_parameter_variations_vs_reference(name, prec, overrides, oracle, reference):
+    """off-default values of the parameters pccb200_seg_params carries: the oracle follows the reference on all of them"""
+    frames = [synth.figure(scale=0.2, seed=3, frame=0), synth.double_sheet(n_side=48, seed=5)]
+    prm = bindings.ctc_seg_params(bits=10, iterations=4, weight=reference.weight_normal(frames[0][0], 11))
+    for k, v in overrides.items():
+        setattr(prm, k, v)
+    ref, _ = reference.encode_gof(frames, prm, occupancy_precision=prec)
+    assert bindings.compare_gof(oracle.encode_gof(frames, prm, occupancy_precision=prec), ref) == []
