@@ -95,3 +95,17 @@ def test_encode_gof_vs_reference_fixture(product):
     for f, (a, b) in enumerate(zip(got, gold["frames"])):
         for k in b:
             assert a[k] == b[k], "frame %d product %s differs from the reference fixture" % (f, k)
+
+
+@pytest.mark.parametrize("name,prec,overrides", [
+    ("patch_splitting", 4, dict(max_patch_size=64)),   # the a9 clamp, which clouds smaller than 1024 never reach at the default
+    ("precision1_thin_levels_cc", 1, dict(surface_thickness=2, min_level=32, min_point_count_per_cc=8)),
+    ("refine_knobs_no_orientation_no_splitting", 4, dict(lambda_refine=1.0, search_radius_refine=96, normal_orientation=0, enable_patch_splitting=0)),
+])
+def test_encode_gof_parameter_variations(name, prec, overrides, oracle, product):
+    """off-default values of the parameters pccb200_seg_params carries (the oracle follows the reference on them: tests/test_oracle.py)"""
+    frames = [synth.figure(scale=0.12, seed=3, frame=0), synth.double_sheet(n_side=32, seed=5)]
+    prm = ctc_seg_params(bits=10, iterations=3, weight=product.weight_normal(frames[0][0], 11))
+    for k, v in overrides.items():
+        setattr(prm, k, v)
+    assert compare_gof(product.encode_gof(frames, prm, occupancy_precision=prec), oracle.encode_gof(frames, prm, occupancy_precision=prec)) == []
