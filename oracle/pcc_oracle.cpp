@@ -1968,4 +1968,86 @@ void pcco_smooth_geometry( int16_t* xyz, uint16_t* boundary, const uint32_t* par
   }
 }
 
+// ---- §8f-1, second stage: colour transfer onto the smoothed cloud, PCCPointSet3::transferColors16bitBP
+// (L/PccLibCommon/source/PCCPointSet.cpp:1126-1485) with the arguments PCCEncoder::encode / PCCDecoder::decode pass
+// (L/PccLibEncoder/source/PCCEncoder.cpp:656-672): filter type 1, search range 0, lossy attributes, 8 forward / 1 backward
+// neighbours, distance-weighted averages, skip-if-identical forward only, distance offsets 4, geometry / colour distance limits
+// beyond their caps (= unlimited), no colour-outlier exclusion. Only the target points the geometry smoothing moved (boundary
+// type 3) get a new colour; `source` is the cloud before smoothing with its 16-bit colours, `target` the smoothed one.
+void pcco_transfer_colors16_smoothed( const int16_t* srcXyz, const uint16_t* srcCol, size_t S, const int16_t* tgtXyz, uint16_t* tgtCol,
+                                      const uint16_t* tgtBoundary, size_t T ) {
+  if ( S == 0 || T == 0 ) return;
+  Tree* treeS = static_cast<Tree*>( pcco_kdtree_build( srcXyz, S ) );
+  Tree* treeT = static_cast<Tree*>( pcco_kdtree_build( tgtXyz, T ) );
+  std::vector<uint16_t> refined( tgtCol, tgtCol + 3 * T );  // forward result per target point
+  std::vector<uint32_t> partSrc;                             // the sampled source points, in sampling order (with repetitions)
+  double                d[8];
+  uint32_t              id[8];
+  auto clip16 = []( double v ) { return uint16_t( v < 0.0 ? 0.0 : ( v > 65535.0 ? 65535.0 : v ) ); };
+  for ( size_t t = 0; t < T; ++t ) {
+    if ( tgtBoundary[t] != 3 ) continue;
+    KnnSet rs( 8, id, d );
+    treeS->search( rs, tgtXyz + 3 * t );
+    const int cnt = rs.cnt;
+    for ( int i = 0; i < cnt; ++i ) partSrc.push_back( id[i] );
+    if ( d[0] < 0.0001 || cnt == 1 ) {
+      for ( int k = 0; k < 3; ++k ) refined[3 * t + k] = srcCol[3 * size_t( id[0] ) + k];
+    } else {
+      double acc[3] = {0.0, 0.0, 0.0}, sum = 0.0;
+      for ( int i = 0; i < cnt; ++i ) {
+        const double wgt = 1 / ( d[i] + 4.0 );
+        for ( int k = 0; k < 3; ++k ) acc[k] += srcCol[3 * size_t( id[i] ) + k] * wgt;
+        sum += wgt;
+      }
+      for ( int k = 0; k < 3; ++k ) refined[3 * t + k] = clip16( std::round( acc[k] / sum ) );
+    }
+  }
+  // backward: every sampled source point votes for its nearest target point if their colours are close
+  struct Vote {
+    double   dist;
+    uint16_t c[3];
+  };
+  std::vector<std::vector<Vote>> votes( T );
+  for ( uint32_t si : partSrc ) {
+    KnnSet rs( 1, id, d );
+    treeT->search( rs, srcXyz + 3 * size_t( si ) );
+    if ( rs.cnt < 1 ) continue;
+    const uint16_t* c  = srcCol + 3 * size_t( si );
+    const uint16_t* tc = tgtCol + 3 * size_t( id[0] );
+    if ( std::abs( int( c[0] ) - int( tc[0] ) ) < 40 && std::abs( int( c[1] ) - int( tc[1] ) ) < 40 && std::abs( int( c[2] ) - int( tc[2] ) ) < 40 )
+      votes[id[0]].push_back( Vote{d[0], {c[0], c[1], c[2]}} );
+  }
+  for ( auto& v : votes ) std::sort( v.begin(), v.end(), []( Vote& a, Vote& b ) { return a.dist < b.dist; } );
+  std::vector<uint16_t> out( tgtCol, tgtCol + 3 * T );
+  for ( size_t t = 0; t < T; ++t ) {
+    if ( tgtBoundary[t] != 3 ) continue;
+    const auto& v = votes[t];
+    if ( v.empty() ) {
+      for ( int k = 0; k < 3; ++k ) out[3 * t + k] = refined[3 * t + k];
+      continue;
+    }
+    double c2[3] = {0.0, 0.0, 0.0};
+    if ( v.size() == 1 ) {
+      for ( int k = 0; k < 3; ++k ) c2[k] = v[0].c[k];
+    } else {
+      double sum = 0.0;
+      for ( auto& e : v ) {
+        const double wgt = 1 / ( std::sqrt( e.dist ) + 4.0 );
+        for ( int k = 0; k < 3; ++k ) c2[k] += ( e.c[k] * wgt );
+        sum += wgt;
+      }
+      for ( int k = 0; k < 3; ++k ) c2[k] /= sum;
+    }
+    for ( int k = 0; k < 3; ++k ) {
+      const double c1 = double( refined[3 * t + k] );
+      double       v0 = std::round( 0.0 * c1 + 1.0 * c2[k] );  // fixWeight: w = 0 (m42538)
+      v0              = v0 < 0.0 ? 0.0 : ( v0 > 65535.0 ? 65535.0 : v0 );
+      out[3 * t + k]  = uint16_t( v0 );
+    }
+  }
+  std::copy( out.begin(), out.end(), tgtCol );
+  pcco_kdtree_free( treeS );
+  pcco_kdtree_free( treeT );
+}
+
 }  // extern "C"

@@ -76,6 +76,11 @@ size_t pcco_gof_get( void* h, int f, int what, void* dst );
 /* ---- §8f-1, first stage: grid-based geometry smoothing of the reconstructed cloud (PCCCodec.cpp:54-150, 982-1106); in place */
 void   pcco_smooth_geometry( int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int grid_size, double threshold );
 
+/* ---- §8f-1, second stage: PCCPointSet3::transferColors16bitBP as encode / decode call it (PCCPointSet.cpp:1126-1485,
+ * PCCEncoder.cpp:656-672): new 16-bit colours for the target points the geometry smoothing moved (boundary type 3); in place */
+void   pcco_transfer_colors16_smoothed( const int16_t* src_xyz, const uint16_t* src_col, size_t ns, const int16_t* tgt_xyz, uint16_t* tgt_col,
+                                        const uint16_t* tgt_boundary, size_t nt );
+
 #ifdef __cplusplus
 }
 #endif

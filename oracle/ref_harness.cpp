@@ -239,6 +239,27 @@ void ref_smooth_geometry( int16_t* xyz, uint16_t* boundary, const uint32_t* part
   }
 }
 
+// PCCPointSet3::transferColors16bitBP with the arguments of PCCEncoder::encode (PCCEncoder.cpp:656-672); target colours in place
+void ref_transfer_colors16_smoothed( const int16_t* srcXyz, const uint16_t* srcCol, size_t S, const int16_t* tgtXyz, uint16_t* tgtCol,
+                                     const uint16_t* tgtBoundary, size_t T ) {
+  Quiet        quiet;
+  PCCPointSet3 source, target;
+  source.resize( S ), source.addColors(), source.addColors16bit();
+  target.resize( T ), target.addColors(), target.addColors16bit();
+  for ( size_t i = 0; i < S; ++i ) {
+    source[i] = PCCPoint3D( srcXyz[3 * i], srcXyz[3 * i + 1], srcXyz[3 * i + 2] );
+    source.setColor16bit( i, PCCColor16bit( srcCol[3 * i], srcCol[3 * i + 1], srcCol[3 * i + 2] ) );
+  }
+  for ( size_t i = 0; i < T; ++i ) {
+    target[i] = PCCPoint3D( tgtXyz[3 * i], tgtXyz[3 * i + 1], tgtXyz[3 * i + 2] );
+    target.setColor16bit( i, PCCColor16bit( tgtCol[3 * i], tgtCol[3 * i + 1], tgtCol[3 * i + 2] ) );
+    target.setBoundaryPointType( i, tgtBoundary[i] );
+  }
+  source.transferColors16bitBP( target, 1, int32_t( 0 ), false, 8, 1, true, true, true, false, 4, 4, 1000, 1000, 1000 * 256, 1000 * 256 );
+  for ( size_t i = 0; i < T; ++i )
+    for ( int d = 0; d < 3; ++d ) tgtCol[3 * i + d] = target.getColor16bit( i )[d];
+}
+
 void ref_weight_normal( const int16_t* xyz, size_t n, int bits, double minW, double w[3] ) {
   Quiet        quiet;
   PCCPointSet3 cloud;

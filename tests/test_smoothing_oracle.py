@@ -34,3 +34,30 @@ def test_oracle_geometry_smoothing_vs_reference(grid, threshold, oracle, referen
         moved += int((want[1] == 3).sum())
     if threshold <= 16.0:
         assert moved > 0   # the case must actually smooth something
+
+
+def transfer(lib, name, src_xyz, src_col, tgt_xyz, tgt_col, tgt_bnd):
+    fn = getattr(lib, name)
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    sx, sc = np.ascontiguousarray(src_xyz, np.int16), np.ascontiguousarray(src_col, np.uint16)
+    tx, tc, tb = np.ascontiguousarray(tgt_xyz, np.int16), np.ascontiguousarray(tgt_col, np.uint16).copy(), np.ascontiguousarray(tgt_bnd, np.uint16)
+    fn(sx.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), len(sx), tx.ctypes.data_as(C.c_void_p), tc.ctypes.data_as(C.c_void_p),
+       tb.ctypes.data_as(C.c_void_p), len(tx))
+    return tc
+
+
+@pytest.mark.parametrize("spread", [257, 3])   # 16-bit colours far apart (the < 40 gate rejects most votes) / close together (most pass)
+def test_oracle_colour_transfer_onto_smoothed_cloud_vs_reference(spread, oracle, reference):
+    """second stage of the chain: PCCPointSet3::transferColors16bitBP as encode / decode call it (PCCPointSet.cpp:1126-1485)"""
+    frames = [synth.figure(scale=0.15, seed=9, frame=0)]
+    prm = bindings.ctc_seg_params(bits=10, iterations=4, weight=oracle.weight_normal(frames[0][0], 11))
+    fr = oracle.encode_gof(frames, prm)[0]
+    xyz, bnd, part = fr.data[6].reshape(-1, 3), fr.data[9], fr.data[8]
+    col16 = fr.data[10].reshape(-1, 3).astype(np.uint16) * spread + 11
+    sm_xyz, sm_bnd = smooth(oracle.lib._dll, "pcco_smooth_geometry", xyz, bnd, part, 8, 64.0)
+    assert int((sm_bnd == 3).sum()) > 1000
+    want = transfer(reference.lib, "ref_transfer_colors16_smoothed", xyz, col16, sm_xyz, col16, sm_bnd)
+    got = transfer(oracle.lib._dll, "pcco_transfer_colors16_smoothed", xyz, col16, sm_xyz, col16, sm_bnd)
+    assert np.array_equal(got, want)
+    assert np.array_equal(want[sm_bnd != 3], col16[sm_bnd != 3]) and int((want != col16).any(axis=1).sum()) > 500
