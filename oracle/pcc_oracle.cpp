@@ -2050,4 +2050,63 @@ void pcco_transfer_colors16_smoothed( const int16_t* srcXyz, const uint16_t* src
   pcco_kdtree_free( treeT );
 }
 
+// ---- §8f-1, the two ends of the chain around colorPointCloud (a gather of these values by pointToPixel):
+// (1) YUV 4:2:0 (8 bit, as decoded) -> YUV 4:4:4 (16 bit): PCCInternalColorConverter "YUV420ToYUV444_8_0", the inverse conversion
+//     of PCCVideoEncoder::compress / PCCVideoDecoder::decompress (L/PccLibColorConverter/source/PCCInternalColorConverter.cpp:
+//     467-485, 595-610, 669-695; up-sampling filter 0, the default; inline filters L/PccLibColorConverter/include/
+//     PCCInternalColorConverter.h:185-247: float accumulation in tap order). in: Y (W*H), U, V ((W/2)*(H/2)); out: 3 planes W*H.
+void pcco_yuv420_to_yuv444_16( const uint8_t* yuv420, size_t W, size_t H, uint16_t* yuv444 ) {
+  const size_t Q = W * H, w2 = W / 2, h2 = H / 2;
+  auto toFloat = [&]( uint8_t v, bool chroma ) {  // YUVtoFloatYUV, one byte per sample
+    const float f = float( ( 1.0 / 255. ) * double( int( v ) - ( chroma ? 128 : 0 ) ) );
+    const float lo = chroma ? -0.5f : 0.f, hi = chroma ? 0.5f : 1.f;
+    return f < lo ? lo : ( f > hi ? hi : f );
+  };
+  auto quantise16 = [&]( float v, bool chroma ) {  // floatYUVToYUV, two bytes per sample
+    float r = std::round( float( 65535. * double( v ) + ( chroma ? 32768. : 0. ) ) );
+    r       = r < 0.f ? 0.f : ( r > 65535.f ? 65535.f : r );
+    return uint16_t( r );
+  };
+  for ( size_t i = 0; i < Q; ++i ) yuv444[i] = quantise16( toFloat( yuv420[i], false ), false );
+  const float ver0[4] = {-8.0f, +64.0f, +216.0f, -16.0f}, hor1[4] = {-16.0f, +144.0f, +144.0f, -16.0f}, ver1[4] = {-16.0f, +216.0f, +64.0f, -8.0f};
+  const float scale = 1.0f / float( 1 << 8 );
+  auto clampI = []( long v, long lo, long hi ) { return v < lo ? lo : ( v > hi ? hi : v ); };
+  for ( int c = 0; c < 2; ++c ) {
+    const uint8_t*     src = yuv420 + Q + size_t( c ) * w2 * h2;
+    std::vector<float> in( w2 * h2 ), tmp( w2 * H );
+    for ( size_t i = 0; i < w2 * h2; ++i ) in[i] = toFloat( src[i], true );
+    for ( size_t i = 0; i < h2; ++i )
+      for ( size_t j = 0; j < w2; ++j ) {
+        float a = 0, b = 0;
+        for ( int t = 0; t < 4; ++t ) a += ver0[t] * in[size_t( clampI( long( i ) + t - 2, 0, long( h2 ) - 1 ) ) * w2 + j];
+        for ( int t = 0; t < 4; ++t ) b += ver1[t] * in[size_t( clampI( long( i ) + 1 + t - 2, 0, long( h2 ) - 1 ) ) * w2 + j];
+        tmp[( 2 * i ) * w2 + j]     = ( a + 0.f ) * scale;
+        tmp[( 2 * i + 1 ) * w2 + j] = ( b + 0.f ) * scale;
+      }
+    uint16_t* dst = yuv444 + Q * ( 1 + c );
+    for ( size_t i = 0; i < H; ++i )
+      for ( size_t j = 0; j < w2; ++j ) {
+        float a = 0, b = 0;
+        a += 0.0f * tmp[i * w2 + size_t( clampI( long( j ) - 1, 0, long( w2 ) - 1 ) )];
+        a += 256.0f * tmp[i * w2 + j];
+        for ( int t = 0; t < 4; ++t ) b += hor1[t] * tmp[i * w2 + size_t( clampI( long( j ) + 1 + t - 2, 0, long( w2 ) - 1 ) )];
+        dst[i * W + 2 * j]     = quantise16( ( a + 0.f ) * scale, true );
+        dst[i * W + 2 * j + 1] = quantise16( ( b + 0.f ) * scale, true );
+      }
+  }
+}
+// (2) PCCPointSet3::convertYUV16ToRGB8 (L/PccLibCommon/include/PCCPointSet.h:133-166): the final 8-bit RGB of every point
+void pcco_yuv16_to_rgb8( const uint16_t* yuv, size_t n, uint8_t* rgb ) {
+  for ( size_t i = 0; i < n; ++i ) {
+    const double wgt = 1.0 / 65535.0;
+    double       y = wgt * double( yuv[3 * i] ), u = wgt * ( double( yuv[3 * i + 1] ) - 32768.0 ), v = wgt * ( double( yuv[3 * i + 2] ) - 32768.0 );
+    y = std::min( std::max( y, 0.0 ), 1.0 ), u = std::min( std::max( u, -0.5 ), 0.5 ), v = std::min( std::max( v, -0.5 ), 0.5 );
+    const double c[3] = {y + 1.57480 * v, y - 0.18733 * u - 0.46813 * v, y + 1.85563 * u};
+    for ( int k = 0; k < 3; ++k ) {
+      const double r = std::round( c[k] * 255 );
+      rgb[3 * i + k] = uint8_t( r < 0.0 ? 0.0 : ( r > 255.0 ? 255.0 : r ) );
+    }
+  }
+}
+
 }  // extern "C"

@@ -81,6 +81,11 @@ void   pcco_smooth_geometry( int16_t* xyz, uint16_t* boundary, const uint32_t* p
 void   pcco_transfer_colors16_smoothed( const int16_t* src_xyz, const uint16_t* src_col, size_t ns, const int16_t* tgt_xyz, uint16_t* tgt_col,
                                         const uint16_t* tgt_boundary, size_t nt );
 
+/* ---- §8f-1, the ends of the chain: decoded 8-bit YUV 4:2:0 frame -> 16-bit YUV 4:4:4 planes (PCCInternalColorConverter
+ * "YUV420ToYUV444_8_0"), and PCCPointSet3::convertYUV16ToRGB8 per point */
+void   pcco_yuv420_to_yuv444_16( const uint8_t* yuv420, size_t width, size_t height, uint16_t* yuv444 );
+void   pcco_yuv16_to_rgb8( const uint16_t* yuv, size_t n, uint8_t* rgb );
+
 #ifdef __cplusplus
 }
 #endif

@@ -260,6 +260,32 @@ void ref_transfer_colors16_smoothed( const int16_t* srcXyz, const uint16_t* srcC
     for ( int d = 0; d < 3; ++d ) tgtCol[3 * i + d] = target.getColor16bit( i )[d];
 }
 
+// PCCInternalColorConverter "YUV420ToYUV444_8_0" on one frame: the inverse conversion after the video codec
+void ref_yuv420_to_yuv444_16( const uint8_t* yuv420, size_t W, size_t H, uint16_t* yuv444 ) {
+  Quiet             quiet;
+  PCCVideoAttribute video;
+  video.resize( 1 );
+  auto& img = video.getFrame( 0 );
+  img.resize( W, H, PCCCOLORFORMAT::YUV420 );
+  const size_t Q = W * H, q4 = ( W / 2 ) * ( H / 2 );
+  img.getChannel( 0 ).assign( yuv420, yuv420 + Q );
+  img.getChannel( 1 ).assign( yuv420 + Q, yuv420 + Q + q4 );
+  img.getChannel( 2 ).assign( yuv420 + Q + q4, yuv420 + Q + 2 * q4 );
+  PCCInternalColorConverter<uint16_t> converter;
+  converter.convert( "YUV420ToYUV444_8_0", video );
+  auto& out = video.getFrame( 0 );
+  for ( int c = 0; c < 3; ++c ) std::copy( out.getChannel( c ).begin(), out.getChannel( c ).end(), yuv444 + c * Q );
+}
+// PCCPointSet3::convertYUV16ToRGB8
+void ref_yuv16_to_rgb8( const uint16_t* yuv, size_t n, uint8_t* rgb ) {
+  PCCPointSet3 ps;
+  ps.resize( n ), ps.addColors(), ps.addColors16bit();
+  for ( size_t i = 0; i < n; ++i ) ps.setColor16bit( i, PCCColor16bit( yuv[3 * i], yuv[3 * i + 1], yuv[3 * i + 2] ) );
+  ps.convertYUV16ToRGB8();
+  for ( size_t i = 0; i < n; ++i )
+    for ( int d = 0; d < 3; ++d ) rgb[3 * i + d] = ps.getColor( i )[d];
+}
+
 void ref_weight_normal( const int16_t* xyz, size_t n, int bits, double minW, double w[3] ) {
   Quiet        quiet;
   PCCPointSet3 cloud;

@@ -61,3 +61,32 @@ def test_oracle_colour_transfer_onto_smoothed_cloud_vs_reference(spread, oracle,
     got = transfer(oracle.lib._dll, "pcco_transfer_colors16_smoothed", xyz, col16, sm_xyz, col16, sm_bnd)
     assert np.array_equal(got, want)
     assert np.array_equal(want[sm_bnd != 3], col16[sm_bnd != 3]) and int((want != col16).any(axis=1).sum()) > 500
+
+
+def test_oracle_inverse_colour_conversion_and_final_rgb_vs_reference(oracle, reference):
+    """the ends of the chain: decoded YUV 4:2:0 -> 16-bit YUV 4:4:4 ("YUV420ToYUV444_8_0") and convertYUV16ToRGB8"""
+    rng = np.random.default_rng(5)
+    W, H = 128, 96
+    smooth_img = (np.add.outer(np.arange(H), np.arange(W)) % 256).astype(np.uint8)
+    for y in (rng.integers(0, 256, W * H * 3 // 2, dtype=np.uint8), np.concatenate([smooth_img.ravel(), smooth_img[::2, ::2].ravel(), 255 - smooth_img[::2, ::2].ravel()])):
+        outs = []
+        for lib, name in ((reference.lib, "ref_yuv420_to_yuv444_16"), (oracle.lib._dll, "pcco_yuv420_to_yuv444_16")):
+            fn = getattr(lib, name)
+            fn.restype = None
+            fn.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+            o = np.zeros(3 * W * H, np.uint16)
+            src = np.ascontiguousarray(y)
+            fn(src.ctypes.data_as(C.c_void_p), W, H, o.ctypes.data_as(C.c_void_p))
+            outs.append(o)
+        assert np.array_equal(outs[0], outs[1])
+    yuv = rng.integers(0, 65536, (50000, 3), dtype=np.uint16)
+    yuv[:100] = [[0, 0, 0]] * 50 + [[65535, 65535, 65535]] * 50
+    outs = []
+    for lib, name in ((reference.lib, "ref_yuv16_to_rgb8"), (oracle.lib._dll, "pcco_yuv16_to_rgb8")):
+        fn = getattr(lib, name)
+        fn.restype = None
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        o = np.zeros((len(yuv), 3), np.uint8)
+        fn(yuv.ctypes.data_as(C.c_void_p), len(yuv), o.ctypes.data_as(C.c_void_p))
+        outs.append(o)
+    assert np.array_equal(outs[0], outs[1])
