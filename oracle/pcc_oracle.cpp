@@ -1837,6 +1837,38 @@ void* pcco_encode_gof_canvas( int nframes, const int16_t* const* xyz, const uint
   return G;
 }
 
+// a13-a15 alone on caller-given patch lists (metadata + block occupancy): the packing of pcco_encode_gof without a segmentation
+void* pcco_pack_gof( int nframes, const int* counts, const pccb200_patch* patches, const uint8_t* occ, const int64_t* occBase, int ra, int bits ) {
+  OGof* G = new OGof();
+  G->frames.resize( nframes );
+  const int occRes = 16, minW = bits + 1 > 11 ? 2560 : 1280, minH = 1280;
+  size_t    at     = 0;
+  for ( int f = 0; f < nframes; ++f ) {
+    auto& P = G->frames[f].pl.patches;
+    P.resize( counts[f] );
+    for ( int i = 0; i < counts[f]; ++i, ++at ) {
+      P[i].m                = patches[at];
+      P[i].m.best_match_idx = -1, P[i].m.is_global = 0, P[i].m.u0 = P[i].m.v0 = P[i].m.orientation = 0;
+      const uint8_t* o = occ + occBase[f] + patches[at].occ_offset;
+      P[i].occ.assign( o, o + size_t( P[i].m.size_u0 ) * P[i].m.size_v0 );
+    }
+    G->frames[f].height = minH;
+    if ( f == 0 || !ra ) packFrame( G->frames[f], occRes, minW, 2, 1.0 );
+    else packFrameAfter( G->frames[f], G->frames[f - 1], occRes, minW, 2, 1.0 );
+  }
+  if ( ra && nframes > 0 && !G->frames[0].pl.patches.empty() ) {
+    size_t tw = minW, th = minH;
+    for ( auto& F : G->frames ) tw = std::max( tw, F.width ), th = std::max( th, F.height );
+    for ( auto& F : G->frames ) F.width = tw, F.height = th;
+    gpaRun( G->frames, occRes, minW, minH );
+  }
+  size_t W = minW, H = minH;
+  for ( auto& F : G->frames ) W = std::max( W, F.width ), H = std::max( H, F.height );
+  W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
+  for ( auto& F : G->frames ) F.width = W, F.height = H;
+  return G;
+}
+
 void pcco_gof_free( void* h ) { delete static_cast<OGof*>( h ); }
 void pcco_gof_dims( void* h, int f, size_t* w, size_t* hgt, size_t* recPoints ) {
   auto& F = static_cast<OGof*>( h )->frames[f];

@@ -68,6 +68,8 @@ void*  pcco_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* c
 /* same with a lower bound on the canvas (frames of one GOF sharded over ranks: pass the all-reduced size) */
 void*  pcco_encode_gof_canvas( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
                                const pccb200_seg_params* p, int occupancy_precision, int stop_after, size_t force_w, size_t force_h );
+/* a13-a15 alone: packing of caller-given patch lists (records + block occupancy, frame f's occupancy bytes start at occ_base[f]) */
+void*  pcco_pack_gof( int nframes, const int* counts, const pccb200_patch* patches, const uint8_t* occ, const int64_t* occ_base, int ra, int bits );
 void   pcco_gof_free( void* h );
 void   pcco_gof_dims( void* h, int f, size_t* w, size_t* hgt, size_t* rec_points );
 void*  pcco_gof_patches( void* h, int f ); /* borrowed patch list for pcco_patches_* */

@@ -664,6 +664,76 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
   return G;
 }
 
+// PCCEncoder::placeSegments (:4762-4835) alone, on patch lists given by the caller (metadata + block occupancy; no clouds, no
+// depth maps): packing tests that do not need a segmentation. `ra` != 0 = constrainedPack + globalPatchAllocation 1.
+void* ref_pack_gof( int nframes, const int* counts, const pccb200_patch* patches, const uint8_t* occ, const int64_t* occBase, int ra, int bits ) {
+  Quiet  quiet;
+  FILE*  devnull  = fopen( "/dev/null", "w" );
+  int    savedOut = dup( 1 );
+  fflush( stdout );
+  dup2( fileno( devnull ), 1 );
+  RefGof* G = new RefGof();
+  G->frames.resize( nframes );
+  {
+    pccb200_seg_params sp{};
+    sp.nn_normal_estimation = 16, sp.normal_orientation = 1, sp.max_nn_count_refine = 1024, sp.iteration_count_refine = 1, sp.voxel_dim_refine = 4;
+    sp.search_radius_refine = 192, sp.occupancy_resolution = 16, sp.enable_patch_splitting = 1, sp.max_patch_size = 1024, sp.quantizer_size_x = 16;
+    sp.quantizer_size_y = 16, sp.min_point_count_per_cc = 16, sp.max_nn_count_patch_seg = 16, sp.surface_thickness = 4, sp.min_level = 64;
+    sp.max_allowed_depth = 255, sp.geometry_bitdepth_2d = 8, sp.geometry_bitdepth_3d = bits + 1, sp.map_count_minus1 = 1;
+    sp.global_patch_allocation = ra ? 1 : 0, sp.lambda_refine = 3.0, sp.max_allowed_dist2_raw_detection = 9.0, sp.max_allowed_dist2_raw_selection = 1.0;
+    PCCEncoderParameters ep;
+    setCtcParams( ep, sp, 4 );
+    ep.check();
+    PCCGroupOfFrames sources;
+    sources.setFrameCount( nframes );
+    PCCLogger  logger;
+    PCCEncoder enc;
+    enc.setLogger( logger );
+    enc.setParameters( ep );
+    PCCContext context;
+    context.addV3CParameterSet( 0 );
+    context.setActiveVpsId( 0 );
+    context.resizeAtlas( 1 );
+    context.setAtlasIndex( 0 );
+    context.resize( nframes );
+    auto&  frames = context.getFrames();
+    size_t at     = 0;
+    for ( int f = 0; f < nframes; ++f ) {
+      auto& fc = frames[f].getTitleFrameContext();
+      fc.setFrameIndex( f );
+      fc.setRawPatchEnabledFlag( false );
+      fc.setUseRawPointsSeparateVideo( false );
+      sources[f].resize( counts[f] ? 1 : 0 );  // (placeSegments only looks at "empty or not")
+      auto& list = fc.getPatches();
+      list.resize( counts[f] );
+      for ( int i = 0; i < counts[f]; ++i, ++at ) {
+        const pccb200_patch& r = patches[at];
+        PCCPatch&            p = list[i];
+        p.setIndex( r.index );
+        p.setViewId( r.view_id );
+        p.setU1( r.u1 ), p.setV1( r.v1 ), p.setD1( r.d1 ), p.setSizeU( r.size_u ), p.setSizeV( r.size_v );
+        p.setSizeU0( r.size_u0 ), p.setSizeV0( r.size_v0 ), p.setOccupancyResolution( 16 );
+        p.getPreGPAPatchData().initialize(), p.getCurGPAPatchData().initialize();
+        std::vector<bool> o( size_t( r.size_u0 ) * r.size_v0 );
+        for ( size_t b = 0; b < o.size(); ++b ) o[b] = occ[occBase[f] + r.occ_offset + b] != 0;
+        p.setOccupancy( o );
+      }
+    }
+    enc.params_.initializeContext( context );
+    enc.placeSegments( sources, context );
+    for ( int f = 0; f < nframes; ++f ) {
+      G->frames[f].patches.patches = context[f].getTile( 0 ).getPatches();
+      G->frames[f].width           = context[f].getAtlasFrameWidth();
+      G->frames[f].height          = context[f].getAtlasFrameHeight();
+    }
+  }
+  fflush( stdout );
+  dup2( savedOut, 1 );
+  close( savedOut );
+  fclose( devnull );
+  return G;
+}
+
 void   ref_gof_free( void* h ) { delete static_cast<RefGof*>( h ); }
 void   ref_gof_seconds( void* h, double* out ) { std::memcpy( out, static_cast<RefGof*>( h )->seconds, 8 * sizeof( double ) ); }
 void   ref_gof_dims( void* h, int f, size_t* w, size_t* hgt, size_t* recPoints ) {
