@@ -5,6 +5,7 @@ drawn so that the runs cover matched / unmatched patches, broken and surviving t
 height, rejected and accepted GPA trials and several sub-contexts per GOF."""
 import ctypes as C
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -98,7 +99,7 @@ CASES = [  # (name, GOFs, frames, patches, max blocks per side, jitter px, churn
     ("small_stable", 6, 8, 30, 6, 6, 0.02),
     ("medium_drifting", 5, 10, 80, 8, 40, 0.08),
     ("crowded", 4, 8, 150, 10, 20, 0.05),           # close to a full 1280 x 1280 canvas
-    ("crowded_mixed", 4, 8, 185, 10, 20, 0.05),     # around the limit: trials accepted for a few frames, then rejected
+    ("crowded_mixed", 4, 10, 205, 10, 20, 0.05),    # around the limit: trials accepted for a few frames, then rejected
     ("crowded_tall", 3, 8, 220, 11, 20, 0.05),      # > 6400 blocks: canvases above 1280, every trial rejected
     ("volatile", 5, 12, 60, 9, 120, 0.35),          # tracks break constantly
     ("huge_patches", 4, 6, 25, 40, 10, 0.05),
@@ -108,7 +109,7 @@ CASES = [  # (name, GOFs, frames, patches, max blocks per side, jitter px, churn
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_packing_fuzz_oracle_and_product_host_logic_vs_reference(case, oracle, reference, shim):  # noqa: F811
     name, gofs, nframes, npatch, size_hi, jitter, churn = case
-    rng = np.random.default_rng(abs(hash(name)) % (2 ** 32))
+    rng = np.random.default_rng(zlib.crc32(name.encode()))   # (deterministic: str hashes are salted per process)
     stats = dict(globals=0, matched=0, tall=0, subcontexts=0)
     for g in range(gofs):
         frames = random_gof(rng, nframes, npatch, size_hi, jitter, churn)
