@@ -1,0 +1,174 @@
+// postrecon.cu — EXPERIMENTAL (not part of include/pccb200.h yet): kernels of the first post-reconstruction stages (SURVEY.md
+// §8f-1) around the host/device functions of postrecon.cuh. The arithmetic is verified on the CPU against the reference
+// (tests/test_postrecon_functions.py); these kernels have NOT run on a GPU yet (round 1 ended without GPU minutes) - the parked
+// test tests/gpu_pending_postrecon.py is the first thing to run next round. Entry points are prefixed pccb200x_.
+#include "postrecon.cuh"
+#include "stages.cuh"
+
+using namespace pccb200;
+
+#include "ctx.cuh"
+
+namespace {
+
+using namespace pccb200::postrecon;
+
+__global__ void kMaxI16( const int16_t* __restrict__ v, size_t n, int* __restrict__ out ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  int          m = i < n ? int( v[i] ) : INT_MIN;
+  m              = __reduce_max_sync( 0xffffffffu, m );
+  if ( ( threadIdx.x & 31 ) == 0 ) atomicMax( out, m );
+}
+__global__ void kMarkCells( const int16_t* __restrict__ xyz, const uint16_t* __restrict__ boundary, size_t n, int gridSize, int w, uint8_t* __restrict__ used ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i >= n || boundary[i] != 1 ) return;
+  const int16_t* p = xyz + 3 * i;
+  if ( nearBorder( p, gridSize, w ) ) return;
+  int S[3];
+  cornerCell( p, gridSize, S );
+  for ( int d = 0; d < 8; ++d ) used[size_t( S[0] + ( d & 1 ) ) + size_t( S[1] + ( ( d >> 1 ) & 1 ) ) * w + size_t( S[2] + ( d >> 2 ) ) * w * w] = 1;
+}
+__global__ void kAccumulateCells( const int16_t* __restrict__ xyz, const uint32_t* __restrict__ partition, size_t n, int gridSize, int w,
+                                  const uint8_t* __restrict__ used, uint32_t* __restrict__ count, int* __restrict__ sum, uint32_t* __restrict__ minPatch,
+                                  uint32_t* __restrict__ maxPatch ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i >= n ) return;
+  const int16_t* p = xyz + 3 * i;
+  if ( nearBorder( p, gridSize, w ) ) return;
+  const size_t c = size_t( p[0] / gridSize ) + size_t( p[1] / gridSize ) * w + size_t( p[2] / gridSize ) * w * w;
+  if ( !used[c] ) return;
+  atomicAdd( &count[c], 1u );
+  atomicAdd( &sum[3 * c], int( p[0] ) ), atomicAdd( &sum[3 * c + 1], int( p[1] ) ), atomicAdd( &sum[3 * c + 2], int( p[2] ) );
+  atomicMin( &minPatch[c], partition[i] + 1 ), atomicMax( &maxPatch[c], partition[i] + 1 );
+}
+__global__ void kSmoothPoints( const int16_t* __restrict__ xyz, const uint16_t* __restrict__ boundary, size_t n, CellGrid g, double threshold,
+                               int16_t* __restrict__ outXyz, uint16_t* __restrict__ outBoundary ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i >= n ) return;
+  const int16_t* p = xyz + 3 * i;
+  int16_t        q[3] = {p[0], p[1], p[2]};
+  uint16_t       b = boundary[i];
+  if ( b == 1 && !nearBorder( p, g.gridSize, g.w ) && smoothPoint( p, g, threshold, q ) ) b = 3;
+  outXyz[3 * i] = q[0], outXyz[3 * i + 1] = q[1], outXyz[3 * i + 2] = q[2];
+  outBoundary[i] = b;
+}
+
+__global__ void kLuma16( const uint8_t* __restrict__ y, size_t Q, uint16_t* __restrict__ out ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i < Q ) out[i] = floatToYuv16( yuv8ToFloat( y[i], false ), false );
+}
+__global__ void kChromaToFloat( const uint8_t* __restrict__ c, size_t n, float* __restrict__ out ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i < n ) out[i] = yuv8ToFloat( c[i], true );
+}
+__global__ void kChromaUpV( const float* __restrict__ in, int w2, int h2, float* __restrict__ tmp ) {
+  const size_t t = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( t >= size_t( w2 ) * h2 ) return;
+  const int i = int( t / w2 ), j = int( t % w2 );
+  upsampleVertical( in, w2, h2, i, j, tmp[size_t( 2 * i ) * w2 + j], tmp[size_t( 2 * i + 1 ) * w2 + j] );
+}
+__global__ void kChromaUpH( const float* __restrict__ tmp, int w2, int H, uint16_t* __restrict__ out ) {
+  const size_t t = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( t >= size_t( w2 ) * H ) return;
+  const int i = int( t / w2 ), j = int( t % w2 );
+  float     e, o;
+  upsampleHorizontal( tmp + size_t( i ) * w2, w2, j, e, o );
+  out[size_t( i ) * ( 2 * w2 ) + 2 * j] = floatToYuv16( e, true ), out[size_t( i ) * ( 2 * w2 ) + 2 * j + 1] = floatToYuv16( o, true );
+}
+__global__ void kYuv16ToRgb8( const uint16_t* __restrict__ yuv, size_t n, uint8_t* __restrict__ rgb ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i >= n ) return;
+  const uint16_t in[3] = {yuv[3 * i], yuv[3 * i + 1], yuv[3 * i + 2]};
+  uint8_t        out[3];
+  yuv16ToRgb8( in, out );
+  rgb[3 * i] = out[0], rgb[3 * i + 1] = out[1], rgb[3 * i + 2] = out[2];
+}
+
+}  // namespace
+
+extern "C" {
+
+// PCCCodec::smoothPointCloudPostprocess (grid smoothing), in place on host arrays: positions n x 3, boundary point types, patch index
+int pccb200x_smooth_geometry( pccb200_ctx* ctx, int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int gridSize, double threshold ) {
+  return guarded( ctx, [&]() -> int {
+    if ( !xyz || !boundary || !partition || gridSize < 2 ) return PCCB200_ERR_BAD_ARG;
+    if ( n == 0 ) return PCCB200_OK;
+    cudaStream_t     s = ctx->stream;
+    DevBuf<int16_t>  dXyz, dOutXyz;
+    DevBuf<uint16_t> dB, dOutB;
+    DevBuf<uint32_t> dPart, dCount, dMin, dMax;
+    DevBuf<int>      dSum, dMaxCoord;
+    DevBuf<uint8_t>  dUsed;
+    dXyz.reserve( 3 * n ), dOutXyz.reserve( 3 * n ), dB.reserve( n ), dOutB.reserve( n ), dPart.reserve( n ), dMaxCoord.reserve( 1 );
+    PCC_CUDA( cudaMemcpyAsync( dXyz, xyz, 3 * n * 2, cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( dB, boundary, n * 2, cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( dPart, partition, n * 4, cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemsetAsync( dMaxCoord, 0, sizeof( int ), s ) );
+    kMaxI16<<<divUp( 3 * n, 256 ), 256, 0, s>>>( dXyz, 3 * n, dMaxCoord );
+    int maxSize = 0;
+    PCC_CUDA( cudaMemcpyAsync( &maxSize, dMaxCoord, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+    streamWait( s );
+    const int    w     = ( maxSize + gridSize - 1 ) / gridSize;
+    const size_t cells = size_t( w ) * w * w;
+    if ( cells == 0 ) return PCCB200_OK;
+    dCount.reserve( cells ), dMin.reserve( cells ), dMax.reserve( cells ), dSum.reserve( 3 * cells ), dUsed.reserve( cells );
+    PCC_CUDA( cudaMemsetAsync( dCount, 0, cells * 4, s ) );
+    PCC_CUDA( cudaMemsetAsync( dMin, 0xff, cells * 4, s ) );
+    PCC_CUDA( cudaMemsetAsync( dMax, 0, cells * 4, s ) );
+    PCC_CUDA( cudaMemsetAsync( dSum, 0, 3 * cells * 4, s ) );
+    PCC_CUDA( cudaMemsetAsync( dUsed, 0, cells, s ) );
+    kMarkCells<<<divUp( n, 256 ), 256, 0, s>>>( dXyz, dB, n, gridSize, w, dUsed );
+    kAccumulateCells<<<divUp( n, 256 ), 256, 0, s>>>( dXyz, dPart, n, gridSize, w, dUsed, dCount, dSum, dMin, dMax );
+    CellGrid g{w, gridSize, dCount, dSum, dMin, dMax, dUsed};
+    kSmoothPoints<<<divUp( n, 256 ), 256, 0, s>>>( dXyz, dB, n, g, threshold, dOutXyz, dOutB );
+    PCC_LAUNCH_CHECK();
+    PCC_CUDA( cudaMemcpyAsync( xyz, dOutXyz, 3 * n * 2, cudaMemcpyDeviceToHost, s ) );
+    PCC_CUDA( cudaMemcpyAsync( boundary, dOutB, n * 2, cudaMemcpyDeviceToHost, s ) );
+    streamWait( s );
+    return PCCB200_OK;
+  } );
+}
+
+// PCCInternalColorConverter "YUV420ToYUV444_8_0": Y (W*H), U, V ((W/2)*(H/2)) bytes -> three W*H planes of uint16
+int pccb200x_yuv420_to_yuv444_16( pccb200_ctx* ctx, const uint8_t* yuv420, size_t W, size_t H, uint16_t* yuv444 ) {
+  return guarded( ctx, [&]() -> int {
+    if ( !yuv420 || !yuv444 || W % 2 || H % 2 || W == 0 || H == 0 ) return PCCB200_ERR_BAD_ARG;
+    cudaStream_t     s = ctx->stream;
+    const size_t     Q = W * H, q4 = ( W / 2 ) * ( H / 2 );
+    const int        w2 = int( W / 2 ), h2 = int( H / 2 );
+    DevBuf<uint8_t>  dIn;
+    DevBuf<uint16_t> dOut;
+    DevBuf<float>    dC, dTmp;
+    dIn.reserve( Q + 2 * q4 ), dOut.reserve( 3 * Q ), dC.reserve( q4 ), dTmp.reserve( 2 * q4 );
+    PCC_CUDA( cudaMemcpyAsync( dIn, yuv420, Q + 2 * q4, cudaMemcpyHostToDevice, s ) );
+    kLuma16<<<divUp( Q, 256 ), 256, 0, s>>>( dIn, Q, dOut );
+    for ( int c = 0; c < 2; ++c ) {
+      kChromaToFloat<<<divUp( q4, 256 ), 256, 0, s>>>( dIn.p + Q + size_t( c ) * q4, q4, dC );
+      kChromaUpV<<<divUp( q4, 256 ), 256, 0, s>>>( dC, w2, h2, dTmp );
+      kChromaUpH<<<divUp( size_t( w2 ) * H, 256 ), 256, 0, s>>>( dTmp, w2, int( H ), dOut.p + Q * ( 1 + c ) );
+    }
+    PCC_LAUNCH_CHECK();
+    PCC_CUDA( cudaMemcpyAsync( yuv444, dOut, 3 * Q * 2, cudaMemcpyDeviceToHost, s ) );
+    streamWait( s );
+    return PCCB200_OK;
+  } );
+}
+
+// PCCPointSet3::convertYUV16ToRGB8 for n points (n x 3 each)
+int pccb200x_yuv16_to_rgb8( pccb200_ctx* ctx, const uint16_t* yuv, size_t n, uint8_t* rgb ) {
+  return guarded( ctx, [&]() -> int {
+    if ( !yuv || !rgb ) return PCCB200_ERR_BAD_ARG;
+    if ( n == 0 ) return PCCB200_OK;
+    cudaStream_t     s = ctx->stream;
+    DevBuf<uint16_t> dIn;
+    DevBuf<uint8_t>  dOut;
+    dIn.reserve( 3 * n ), dOut.reserve( 3 * n );
+    PCC_CUDA( cudaMemcpyAsync( dIn, yuv, 3 * n * 2, cudaMemcpyHostToDevice, s ) );
+    kYuv16ToRgb8<<<divUp( n, 256 ), 256, 0, s>>>( dIn, n, dOut );
+    PCC_LAUNCH_CHECK();
+    PCC_CUDA( cudaMemcpyAsync( rgb, dOut, 3 * n, cudaMemcpyDeviceToHost, s ) );
+    streamWait( s );
+    return PCCB200_OK;
+  } );
+}
+}
