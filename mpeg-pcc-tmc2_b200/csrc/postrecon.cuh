@@ -12,6 +12,8 @@
 
 #include <cmath>
 
+#include "stdsort.cuh"
+
 #if defined( __CUDACC__ )
 #define PCC_HD __host__ __device__
 #else
@@ -126,6 +128,58 @@ PCC_HD inline void yuv16ToRgb8( const uint16_t yuv[3], uint8_t rgb[3] ) {
   for ( int k = 0; k < 3; ++k ) {
     const double r = round( c[k] * 255 );
     rgb[k]         = uint8_t( r < 0.0 ? 0.0 : ( r > 255.0 ? 255.0 : r ) );
+  }
+}
+
+// ---- colour transfer onto the smoothed cloud: PCCPointSet3::transferColors16bitBP with the arguments of encode / decode
+// (PccLibCommon/source/PCCPointSet.cpp:1126-1485; PccLibEncoder/source/PCCEncoder.cpp:656-672), per target point of boundary type 3
+// forward: the (up to 8) nearest source points of the target, nanoflann order, squared distances
+PCC_HD inline void forwardColour( const uint32_t* id, const float* dist2, int cnt, const uint16_t* srcCol, uint16_t out[3] ) {
+  if ( double( dist2[0] ) < 0.0001 || cnt == 1 ) {
+    for ( int k = 0; k < 3; ++k ) out[k] = srcCol[3 * size_t( id[0] ) + k];
+    return;
+  }
+  double acc[3] = {0.0, 0.0, 0.0}, sum = 0.0;
+  for ( int i = 0; i < cnt; ++i ) {
+    const double wgt = 1 / ( double( dist2[i] ) + 4.0 );
+    for ( int k = 0; k < 3; ++k ) acc[k] += srcCol[3 * size_t( id[i] ) + k] * wgt;
+    sum += wgt;
+  }
+  for ( int k = 0; k < 3; ++k ) {
+    const double r = round( acc[k] / sum );
+    out[k]         = uint16_t( r < 0.0 ? 0.0 : ( r > 65535.0 ? 65535.0 : r ) );
+  }
+}
+// backward: the votes a target received (in sampling order), sorted as std::sort sorts them, distance-weighted mean
+struct Vote {
+  double   dist;  // squared distance source sample -> target
+  uint16_t c[3];
+};
+struct VoteByDistance {
+  PCC_HD bool operator()( const Vote& a, const Vote& b ) const { return a.dist < b.dist; }
+};
+PCC_HD inline void backwardColour( Vote* votes, int n, const uint16_t refined[3], uint16_t out[3] ) {
+  if ( n == 0 ) {
+    for ( int k = 0; k < 3; ++k ) out[k] = refined[k];
+    return;
+  }
+  stdsort::sort( votes, votes + n, VoteByDistance() );
+  double c2[3] = {0.0, 0.0, 0.0};
+  if ( n == 1 ) {
+    for ( int k = 0; k < 3; ++k ) c2[k] = votes[0].c[k];
+  } else {
+    double sum = 0.0;
+    for ( int i = 0; i < n; ++i ) {
+      const double wgt = 1 / ( sqrt( votes[i].dist ) + 4.0 );
+      for ( int k = 0; k < 3; ++k ) c2[k] += ( votes[i].c[k] * wgt );
+      sum += wgt;
+    }
+    for ( int k = 0; k < 3; ++k ) c2[k] /= sum;
+  }
+  for ( int k = 0; k < 3; ++k ) {
+    double v = round( 0.0 * double( refined[k] ) + 1.0 * c2[k] );  // fixWeight: w = 0
+    v        = v < 0.0 ? 0.0 : ( v > 65535.0 ? 65535.0 : v );
+    out[k]   = uint16_t( v );
   }
 }
 

@@ -75,4 +75,22 @@ void prx_yuv420_to_yuv444_16( const uint8_t* yuv420, size_t W, size_t H, uint16_
 void prx_yuv16_to_rgb8( const uint16_t* yuv, size_t n, uint8_t* rgb ) {
   for ( size_t i = 0; i < n; ++i ) yuv16ToRgb8( yuv + 3 * i, rgb + 3 * i );
 }
+
+// per target t of `count` targets: forward colour from its neighbour row (k entries, 0xFFFFFFFF = none)
+void prx_forward( const uint32_t* idx, const float* dist2, int k, size_t count, const uint16_t* srcCol, uint16_t* out ) {
+  for ( size_t t = 0; t < count; ++t ) {
+    int cnt = 0;
+    while ( cnt < k && idx[t * k + cnt] != 0xFFFFFFFFu ) ++cnt;
+    forwardColour( idx + t * k, dist2 + t * k, cnt, srcCol, out + 3 * t );
+  }
+}
+// votes in CSR form (offsets per target, entries in sampling order): (dist, colour); refined = forward colours; out = final colours
+void prx_backward( const uint64_t* offsets, const double* voteDist, const uint16_t* voteCol, size_t count, const uint16_t* refined, uint16_t* out ) {
+  std::vector<Vote> v;
+  for ( size_t t = 0; t < count; ++t ) {
+    v.clear();
+    for ( uint64_t e = offsets[t]; e < offsets[t + 1]; ++e ) v.push_back( Vote{voteDist[e], {voteCol[3 * e], voteCol[3 * e + 1], voteCol[3 * e + 2]}} );
+    backwardColour( v.data(), int( v.size() ), refined + 3 * t, out + 3 * t );
+  }
+}
 }
