@@ -2,6 +2,8 @@
 // §8f-1) around the host/device functions of postrecon.cuh. The arithmetic is verified on the CPU against the reference
 // (tests/test_postrecon_functions.py); these kernels have NOT run on a GPU yet (round 1 ended without GPU minutes) - the parked
 // test tests/gpu_pending_postrecon.py is the first thing to run next round. Entry points are prefixed pccb200x_.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "postrecon.cuh"
 #include "stages.cuh"
 
@@ -84,9 +86,140 @@ __global__ void kYuv16ToRgb8( const uint16_t* __restrict__ yuv, size_t n, uint8_
   rgb[3 * i] = out[0], rgb[3 * i + 1] = out[1], rgb[3 * i + 2] = out[2];
 }
 
+// ---- colour transfer onto the smoothed cloud (transferColors16bitBP as encode / decode call it) ---------------------------------
+__global__ void kFlagMoved( const uint16_t* __restrict__ boundary, size_t n, uint32_t* __restrict__ flag ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i < n ) flag[i] = boundary[i] == 3 ? 1u : 0u;
+}
+__global__ void kListMoved( const uint32_t* __restrict__ flag, const uint32_t* __restrict__ scan, size_t n, const short4* __restrict__ tgt4,
+                            uint32_t* __restrict__ moved, short4* __restrict__ queries ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i < n && flag[i] ) moved[scan[i]] = uint32_t( i ), queries[scan[i]] = tgt4[i];
+}
+__global__ void kForwardColours( const uint32_t* __restrict__ fidx, const float* __restrict__ fdist, size_t M, const uint16_t* __restrict__ srcCol,
+                                 uint16_t* __restrict__ refined ) {
+  const size_t m = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( m >= M ) return;
+  uint32_t id[8];
+  float    d[8];
+  int      cnt = 0;
+  for ( int i = 0; i < 8; ++i ) {
+    id[i] = fidx[8 * m + i], d[i] = fdist[8 * m + i];
+    if ( id[i] != 0xFFFFFFFFu && cnt == i ) ++cnt;
+  }
+  uint16_t out[3];
+  forwardColour( id, d, cnt, srcCol, out );
+  refined[3 * m] = out[0], refined[3 * m + 1] = out[1], refined[3 * m + 2] = out[2];
+}
+// the sampled source points (row-major over the moved targets' neighbour rows: the reference's sampling order) as 1-NN queries
+__global__ void kSampleQueries( const uint32_t* __restrict__ fidx, size_t E, const short4* __restrict__ src4, short4* __restrict__ q ) {
+  const size_t e = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( e < E ) q[e] = src4[fidx[e] != 0xFFFFFFFFu ? fidx[e] : 0u];
+}
+__global__ void kVoteKeys16( const uint32_t* __restrict__ fidx, const uint32_t* __restrict__ bidx, size_t E, const uint16_t* __restrict__ srcCol,
+                             const uint16_t* __restrict__ tgtCol, const uint16_t* __restrict__ tgtBoundary, uint32_t* __restrict__ keys,
+                             uint32_t* __restrict__ vals ) {
+  const size_t e = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( e >= E ) return;
+  uint32_t key = 0xFFFFFFFFu;
+  const uint32_t si = fidx[e];
+  if ( si != 0xFFFFFFFFu ) {
+    const uint32_t t = bidx[e];
+    if ( t != 0xFFFFFFFFu && tgtBoundary[t] == 3 ) {  // (votes for targets that keep their colour are never read)
+      bool close = true;
+      for ( int k = 0; k < 3; ++k ) close = close && abs( int( srcCol[3 * size_t( si ) + k] ) - int( tgtCol[3 * size_t( t ) + k] ) ) < 40;
+      if ( close ) key = t;
+    }
+  }
+  keys[e] = key, vals[e] = uint32_t( e );
+}
+__device__ __forceinline__ size_t lowerBound( const uint32_t* a, size_t n, uint32_t v ) {
+  size_t lo = 0, hi = n;
+  while ( lo < hi ) {
+    const size_t mid = ( lo + hi ) / 2;
+    if ( a[mid] < v ) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+__global__ void kBackwardColours( const uint32_t* __restrict__ moved, size_t M, const uint32_t* __restrict__ sortedKeys, const uint32_t* __restrict__ sortedVals,
+                                  size_t E, const uint32_t* __restrict__ fidx, const float* __restrict__ bdist, const uint16_t* __restrict__ srcCol,
+                                  const uint16_t* __restrict__ refined, Vote* __restrict__ votes, uint16_t* __restrict__ outCol ) {
+  const size_t m = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( m >= M ) return;
+  const uint32_t t = moved[m];
+  const size_t   a = lowerBound( sortedKeys, E, t ), b = lowerBound( sortedKeys, E, t + 1 );
+  for ( size_t j = a; j < b; ++j ) {  // radix sort is stable: the votes of a target are in sampling order
+    const uint32_t e = sortedVals[j], si = fidx[e];
+    votes[j]         = Vote{double( bdist[e] ), {srcCol[3 * size_t( si )], srcCol[3 * size_t( si ) + 1], srcCol[3 * size_t( si ) + 2]}};
+  }
+  uint16_t out[3];
+  const uint16_t ref[3] = {refined[3 * m], refined[3 * m + 1], refined[3 * m + 2]};
+  backwardColour( votes + a, int( b - a ), ref, out );
+  outCol[3 * size_t( t )] = out[0], outCol[3 * size_t( t ) + 1] = out[1], outCol[3 * size_t( t ) + 2] = out[2];
+}
+
 }  // namespace
 
 extern "C" {
+
+// PCCPointSet3::transferColors16bitBP as encode / decode call it: new 16-bit colours (in place) for the target points of boundary type 3
+int pccb200x_transfer_colors16_smoothed( pccb200_ctx* ctx, const int16_t* srcXyz, const uint16_t* srcCol, size_t S, const int16_t* tgtXyz,
+                                         uint16_t* tgtCol, const uint16_t* tgtBoundary, size_t T ) {
+  return guarded( ctx, [&]() -> int {
+    if ( !srcXyz || !srcCol || !tgtXyz || !tgtCol || !tgtBoundary ) return PCCB200_ERR_BAD_ARG;
+    if ( S == 0 || T == 0 ) return PCCB200_OK;
+    cudaStream_t     s = ctx->stream;
+    DevBuf<int16_t>  raw;
+    DevBuf<short4>   src4, tgt4, q4, sq4;
+    DevBuf<uint16_t> dSrcCol, dTgtCol, dOutCol, dB, dRefined;
+    DevBuf<uint32_t> flag, scan, scanTmp, moved, fidx, bidx, keysA, keysB, valsA, valsB;
+    DevBuf<float>    fdist, bdist;
+    DevBuf<uint8_t>  cubTmp;
+    DevBuf<Vote>     votes;
+    KdTree           treeS, treeT;
+    raw.reserve( 3 * std::max( S, T ) ), src4.reserve( S + 1 ), tgt4.reserve( T + 1 );
+    PCC_CUDA( cudaMemcpyAsync( raw, srcXyz, 3 * S * 2, cudaMemcpyHostToDevice, s ) );
+    packXyz( raw, S, src4, s );
+    streamWait( s );
+    PCC_CUDA( cudaMemcpyAsync( raw, tgtXyz, 3 * T * 2, cudaMemcpyHostToDevice, s ) );
+    packXyz( raw, T, tgt4, s );
+    dSrcCol.reserve( 3 * S ), dTgtCol.reserve( 3 * T ), dOutCol.reserve( 3 * T ), dB.reserve( T );
+    PCC_CUDA( cudaMemcpyAsync( dSrcCol, srcCol, 3 * S * 2, cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( dTgtCol, tgtCol, 3 * T * 2, cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( dOutCol, tgtCol, 3 * T * 2, cudaMemcpyHostToDevice, s ) );
+    PCC_CUDA( cudaMemcpyAsync( dB, tgtBoundary, T * 2, cudaMemcpyHostToDevice, s ) );
+    kdBuild( treeS, src4, S, s );
+    kdBuild( treeT, tgt4, T, s );
+    // the targets the smoothing moved, in index order
+    flag.reserve( T + 1 ), scan.reserve( T + 2 ), scanTmp.reserve( scanTmpElems( T ) );
+    kFlagMoved<<<divUp( T, 256 ), 256, 0, s>>>( dB, T, flag );
+    exclusiveScanU32( flag, scan, T, scanTmp, s );
+    uint32_t M = 0;
+    PCC_CUDA( cudaMemcpyAsync( &M, scan.p + T, sizeof( uint32_t ), cudaMemcpyDeviceToHost, s ) );
+    streamWait( s );
+    if ( M == 0 ) return PCCB200_OK;
+    const size_t E = size_t( M ) * 8;
+    moved.reserve( M ), q4.reserve( M ), fidx.reserve( E ), fdist.reserve( E ), dRefined.reserve( 3 * size_t( M ) );
+    kListMoved<<<divUp( T, 256 ), 256, 0, s>>>( flag, scan, T, tgt4, moved, q4 );
+    kdKnn( treeS, q4, M, nullptr, 8, fidx, fdist, s );
+    kForwardColours<<<divUp( M, 128 ), 128, 0, s>>>( fidx, fdist, M, dSrcCol, dRefined );
+    // backward votes
+    sq4.reserve( E ), bidx.reserve( E ), bdist.reserve( E ), keysA.reserve( E ), keysB.reserve( E ), valsA.reserve( E ), valsB.reserve( E ), votes.reserve( E );
+    kSampleQueries<<<divUp( E, 256 ), 256, 0, s>>>( fidx, E, src4, sq4 );
+    kdKnn( treeT, sq4, E, nullptr, 1, bidx, bdist, s );
+    kVoteKeys16<<<divUp( E, 256 ), 256, 0, s>>>( fidx, bidx, E, dSrcCol, dTgtCol, dB, keysA, valsA );
+    size_t tmpBytes = 0;
+    PCC_CUDA( cub::DeviceRadixSort::SortPairs( nullptr, tmpBytes, keysA.p, keysB.p, valsA.p, valsB.p, int( E ), 0, 32, s ) );
+    cubTmp.reserve( tmpBytes + 16 );
+    PCC_CUDA( cub::DeviceRadixSort::SortPairs( cubTmp.p, tmpBytes, keysA.p, keysB.p, valsA.p, valsB.p, int( E ), 0, 32, s ) );
+    kBackwardColours<<<divUp( M, 128 ), 128, 0, s>>>( moved, M, keysB, valsB, E, fidx, bdist, dSrcCol, dRefined, votes, dOutCol );
+    PCC_LAUNCH_CHECK();
+    PCC_CUDA( cudaMemcpyAsync( tgtCol, dOutCol, 3 * T * 2, cudaMemcpyDeviceToHost, s ) );
+    streamWait( s );
+    return PCCB200_OK;
+  } );
+}
 
 // PCCCodec::smoothPointCloudPostprocess (grid smoothing), in place on host arrays: positions n x 3, boundary point types, patch index
 int pccb200x_smooth_geometry( pccb200_ctx* ctx, int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int gridSize, double threshold ) {

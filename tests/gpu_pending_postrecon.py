@@ -52,3 +52,22 @@ def test_gpu_colour_conversions_vs_oracle(oracle, product):
     g.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     assert g(product.ctx, yuv.ctypes.data_as(C.c_void_p), len(yuv), got.ctypes.data_as(C.c_void_p)) == 0
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("spread", [257, 3])
+def test_gpu_colour_transfer_onto_smoothed_cloud_vs_oracle(spread, oracle, product):
+    from test_smoothing_oracle import transfer
+    frames = [synth.figure(scale=0.15, seed=9, frame=0)]
+    prm = bindings.ctc_seg_params(bits=10, iterations=4, weight=oracle.weight_normal(frames[0][0], 11))
+    fr = oracle.encode_gof(frames, prm)[0]
+    xyz, bnd, part = fr.data[6].reshape(-1, 3), fr.data[9], fr.data[8]
+    col16 = (fr.data[10].reshape(-1, 3).astype(np.uint16) * spread + 11).astype(np.uint16)
+    sm_xyz, sm_bnd = smooth(oracle.lib._dll, "pcco_smooth_geometry", xyz, bnd, part, 8, 64.0)
+    want = transfer(oracle.lib._dll, "pcco_transfer_colors16_smoothed", xyz, col16, sm_xyz, col16, sm_bnd)
+    fn = product.lib.pccb200x_transfer_colors16_smoothed
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    sx, sc = np.ascontiguousarray(xyz, np.int16), np.ascontiguousarray(col16)
+    tx, tc, tb = np.ascontiguousarray(sm_xyz, np.int16), col16.copy(), np.ascontiguousarray(sm_bnd, np.uint16)
+    assert fn(product.ctx, sx.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), len(sx), tx.ctypes.data_as(C.c_void_p),
+              tc.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), len(tx)) == 0
+    assert np.array_equal(tc, want)
