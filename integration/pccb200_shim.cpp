@@ -238,4 +238,57 @@ int stageB2( Session& s, PCCContext& context ) {
   return PCCB200_OK;
 }
 
+int decodeFrame( Session& s, PCCContext& context, size_t frameIdx, size_t occupancyPrecision, PCCPointSet3& reconstruct,
+                 std::vector<uint32_t>& partition ) {
+  if ( !s.ctx ) {
+    const int rc = pccb200_create( 0, &s.ctx );
+    if ( rc != PCCB200_OK ) return rc;
+  }
+  auto&        tile = context[frameIdx].getTile( 0 );
+  auto&        om   = context.getVideoOccupancyMap().getFrame( frameIdx );
+  auto&        geo  = context.getVideoGeometryMultiple()[0];
+  const size_t W = geo.getFrame( 2 * frameIdx ).getWidth(), H = geo.getFrame( 2 * frameIdx ).getHeight();
+  // the fields the decoder rebuilds from the atlas syntax (PCCDecoder.cpp:900-1040) are all pccb200_generate_point_cloud reads
+  std::vector<pccb200_patch> recs( tile.getPatches().size() );
+  for ( size_t i = 0; i < recs.size(); ++i ) {
+    const PCCPatch& p = tile.getPatches()[i];
+    pccb200_patch&  r = recs[i];
+    r                 = pccb200_patch{};
+    r.index = int32_t( i ), r.view_id = int32_t( p.getViewId() );
+    r.u1 = int32_t( p.getU1() ), r.v1 = int32_t( p.getV1() ), r.d1 = int32_t( p.getD1() );
+    r.size_u = int32_t( p.getSizeU0() * 16 ), r.size_v = int32_t( p.getSizeV0() * 16 );
+    r.size_u0 = int32_t( p.getSizeU0() ), r.size_v0 = int32_t( p.getSizeV0() );
+    r.u0 = int32_t( p.getU0() ), r.v0 = int32_t( p.getV0() ), r.orientation = int32_t( p.getPatchOrientation() );
+    r.best_match_idx = -1;
+  }
+  const std::vector<uint8_t>&  occ = om.getChannel( 0 );
+  const std::vector<uint16_t>& g0  = geo.getFrame( 2 * frameIdx ).getChannel( 0 );
+  const std::vector<uint16_t>& g1  = geo.getFrame( 2 * frameIdx + 1 ).getChannel( 0 );
+  size_t                       R   = 0;
+  int rc = pccb200_generate_point_cloud( s.ctx, recs.data(), int( recs.size() ), occ.data(), g0.data(), g1.data(), W, H, int( occupancyPrecision ), 0,
+                                         nullptr, nullptr, nullptr, nullptr, &R );
+  if ( rc != PCCB200_OK ) return rc;
+  std::vector<int16_t>  xyz( 3 * R );
+  std::vector<uint32_t> p2p( 3 * R );
+  std::vector<uint16_t> bnd( R );
+  partition.assign( R, 0 );
+  rc = pccb200_generate_point_cloud( s.ctx, recs.data(), int( recs.size() ), occ.data(), g0.data(), g1.data(), W, H, int( occupancyPrecision ), R,
+                                     xyz.data(), p2p.data(), partition.data(), bnd.data(), &R );
+  if ( rc != PCCB200_OK ) return rc;
+  reconstruct.clear();
+  reconstruct.resize( R );
+  auto& pointToPixel = tile.getPointToPixel();
+  pointToPixel.resize( R );
+  for ( size_t i = 0; i < R; ++i ) {
+    reconstruct[i] = PCCPoint3D( xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2] );
+    reconstruct.setBoundaryPointType( i, bnd[i] );
+    pointToPixel[i] = PCCVector3<size_t>( p2p[3 * i], p2p[3 * i + 1], p2p[3 * i + 2] );
+  }
+  auto& map = tile.getOccupancyMap();  // block-precision occupancy, as generatePointCloud leaves it (PCCCodec.cpp:559-572)
+  map.assign( W * H, 0 );
+  for ( size_t y = 0; y < H; ++y )
+    for ( size_t x = 0; x < W; ++x ) map[y * W + x] = occ[( y / occupancyPrecision ) * ( W / occupancyPrecision ) + x / occupancyPrecision];
+  return PCCB200_OK;
+}
+
 }  // namespace pccb200shim

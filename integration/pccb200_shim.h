@@ -37,4 +37,13 @@ int stageB1( Session& s, const pcc::PCCEncoderParameters& params, pcc::PCCContex
              std::vector<std::vector<uint32_t>>& partitions );
 int stageB2( Session& s, pcc::PCCContext& context );
 
+// Decoder side (PccLibDecoder/source/PCCDecoder.cpp:320-351): drop-in body for the per-frame block
+//   generateBlockToPatchFromOccupancyMapVideo( ... ) + generatePointCloud( tileReconstrct, context, frameIdx, tileIdx, gpcParams, partition, true )
+// for the CTC reconstruction options (two maps, absolute D1, duplicate removal, no EOM / PLR / raw patches, one tile): the patches of
+// the tile as the decoder rebuilt them from the atlas syntax, the decoded occupancy and geometry frames of `context`; fills
+// `reconstruct` (positions + boundary point types), tile.getPointToPixel(), tile.getOccupancyMap() (the
+// block-precision map generatePointCloud leaves there) and `partition`. Needs s.ctx only (no GOF).
+int decodeFrame( Session& s, pcc::PCCContext& context, size_t frameIdx, size_t occupancyPrecision, pcc::PCCPointSet3& reconstruct,
+                 std::vector<uint32_t>& partition );
+
 }  // namespace pccb200shim

@@ -536,9 +536,10 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
       fc.setLog2PatchQuantizerSizeY( enc.params_.log2QuantizerSizeY_ );
     }
     const RefHotPathHooks* hooks = gHooks;
+    const bool             hookA = hooks && hooks->stageA, hookB1 = hooks && hooks->stageB1, hookB2 = hooks && hooks->stageB2;
     int                    hookError = 0;
     auto t0 = clk::now();
-    if ( hooks ) {
+    if ( hookA ) {
       hookError = hooks->stageA( enc, sources, context );  // :103-172 through the external implementation
     } else {
       enc.generateSegments( sources, context );  // :103
@@ -561,7 +562,7 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
     }
     if ( stopAfter != 1 ) {
       t0 = clk::now();
-      if ( !hooks ) {
+      if ( !hookA ) {
         enc.generateOccupancyMap( context, true );         // :133
         enc.generateOccupancyMapVideo( sources, context );  // :139  (compress skipped: lossless)
         enc.generateBlockToPatchFromOccupancyMapVideo( context, enc.params_.occupancyResolution_, enc.params_.occupancyPrecision_ );  // :168
@@ -577,7 +578,7 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
         R.blockToPatch.assign( b2p.begin(), b2p.end() );
       }
       t0 = clk::now();
-      if ( !hooks ) enc.generateGeometryVideo( sources, context );  // :172
+      if ( !hookA ) enc.generateGeometryVideo( sources, context );  // :172
       G->seconds[3] = secs( t0 );
       for ( int f = 0; f < nframes; ++f )
         for ( int m = 0; m < 2; ++m ) {
@@ -591,7 +592,7 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
       enc.setGeneratePointCloudParameters( gpc, context );  // :315
       context.allocOneLayerData();
       std::vector<std::vector<uint32_t>> partitions( context.size() );
-      if ( hooks ) {
+      if ( hookB1 ) {
         hooks->stageB1( enc, context, reconstructs, partitions );  // :319-341 through the external implementation
       } else {
         for ( size_t f = 0; f < context.size(); f++ ) {
@@ -619,7 +620,7 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
     }
     if ( stopAfter == 0 ) {
       t0 = clk::now();
-      if ( !hooks ) enc.generateAttributeVideo( sources, reconstructs, context, enc.params_ );  // :341
+      if ( !hookB1 ) enc.generateAttributeVideo( sources, reconstructs, context, enc.params_ );  // :341
       G->seconds[5] = secs( t0 );
       auto& video = context.getVideoAttributesMultiple()[0];
       for ( int f = 0; f < nframes; ++f ) {
@@ -632,7 +633,7 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
           for ( int d = 0; d < 3; ++d ) R.recRgb[3 * i + d] = rec.getColor( i )[d];
       }
       t0 = clk::now();
-      if ( hooks ) {
+      if ( hookB2 ) {
         hooks->stageB2( enc, context );  // :344-424 through the external implementation
       } else {
         for ( int f = 0; f < nframes; ++f )

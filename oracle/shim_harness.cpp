@@ -34,6 +34,19 @@ int hookB1( PCCEncoder& enc, PCCContext& context, PCCGroupOfFrames& reconstructs
 }
 int hookB2( PCCEncoder&, PCCContext& context ) { return gLastCode = pccb200shim::stageB2( *gSession, context ); }
 const RefHotPathHooks kHooks = {hookA, hookB1, hookB2};
+// decoder-side binding: the reference's own encoder stages up to the geometry video, then every frame reconstructed by
+// pccb200shim::decodeFrame (what PCCDecoder::decode would call in place of generatePointCloud)
+int hookDecode( PCCEncoder& enc, PCCContext& context, PCCGroupOfFrames& reconstructs, std::vector<std::vector<uint32_t>>& partitions ) {
+  for ( size_t f = 0; f < context.size(); ++f ) {
+    PCCPointSet3 rec;
+    gLastCode = pccb200shim::decodeFrame( *gSession, context, f, enc.params_.occupancyPrecision_, rec, partitions[f] );
+    if ( gLastCode != 0 ) return gLastCode;
+    reconstructs[f].clear();
+    reconstructs[f].appendPointSet( rec );
+  }
+  return 0;
+}
+const RefHotPathHooks kDecodeHooks = {nullptr, hookDecode, nullptr};
 }  // namespace
 
 extern "C" {
@@ -44,6 +57,19 @@ void* shim_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* co
   gSession  = &session;
   gLastCode = 0;
   ref_set_hot_path_hooks( &kHooks );
+  void* h = ref_encode_gof( nframes, xyz, rgb, n, p, occupancyPrecision, stopAfter );
+  ref_set_hot_path_hooks( nullptr );
+  gSession = nullptr;
+  if ( code ) *code = gLastCode;
+  return h;
+}
+// reference stages up to the geometry images, reconstruction through the decoder-side binding (use stopAfter = 3)
+void* shim_decode_gof( int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n, const pccb200_seg_params* p,
+                       int occupancyPrecision, int stopAfter, int* code ) {
+  pccb200shim::Session session;
+  gSession  = &session;
+  gLastCode = 0;
+  ref_set_hot_path_hooks( &kDecodeHooks );
   void* h = ref_encode_gof( nframes, xyz, rgb, n, p, occupancyPrecision, stopAfter );
   ref_set_hot_path_hooks( nullptr );
   gSession = nullptr;

@@ -504,7 +504,12 @@ class Shim:
     def available():
         return os.path.exists(SHIM_SO) and os.path.exists(REF_SO) and os.path.exists(PRODUCT_SO)
 
-    def encode_gof(self, frames, params, occupancy_precision=4, stop_after=0):
+    def decode_gof(self, frames, params, occupancy_precision=4):
+        """the reference's stages up to the geometry images, then every frame reconstructed through the decoder-side binding
+        (pccb200shim::decodeFrame); products up to generatePointCloud (stop_after = 3)"""
+        return self.encode_gof(frames, params, occupancy_precision, 3, entry="shim_decode_gof")
+
+    def encode_gof(self, frames, params, occupancy_precision=4, stop_after=0, entry="shim_encode_gof"):
         """returns (list of GofFrame, status code of the last pccb200 call; frames are empty when the hot path failed)"""
         L = self.ref.lib
         L.ref_gof_free.argtypes = [C.c_void_p]
@@ -515,7 +520,9 @@ class Shim:
         L.ref_gof_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         n, xs, cs, xp, cp, ns = _frames_args(frames)
         code = C.c_int(0)
-        h = self.lib.shim_encode_gof(n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after, C.byref(code))
+        fn = getattr(self.lib, entry)
+        fn.restype, fn.argtypes = self.lib.shim_encode_gof.restype, self.lib.shim_encode_gof.argtypes
+        h = fn(n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after, C.byref(code))
         out = []
         if code.value == 0:
             for f in range(n):

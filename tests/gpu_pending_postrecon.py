@@ -71,3 +71,17 @@ def test_gpu_colour_transfer_onto_smoothed_cloud_vs_oracle(spread, oracle, produ
     assert fn(product.ctx, sx.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), len(sx), tx.ctypes.data_as(C.c_void_p),
               tc.ctypes.data_as(C.c_void_p), tb.ctypes.data_as(C.c_void_p), len(tx)) == 0
     assert np.array_equal(tc, want)
+
+
+def test_gpu_decoder_side_binding_vs_reference():
+    """integration/pccb200_shim.cpp decodeFrame (what PCCDecoder::decode would call instead of generatePointCloud): the reference's
+    own encoder stages produce patches + occupancy + geometry frames, the reconstruction then comes from the decoder-side binding"""
+    shim = bindings.Shim()
+    frames = [synth.figure(scale=0.12, seed=4, frame=f) for f in range(2)] + [synth.double_sheet(n_side=32, seed=2)]
+    prm = bindings.ctc_seg_params(bits=10, iterations=4, weight=(1.0, 1.0, 1.0))
+    want, _ = shim.ref.encode_gof(frames, prm, stop_after=3)
+    got, code = shim.decode_gof(frames, prm)
+    assert code == 0
+    for a, b in zip(got, want):
+        for what in (6, 7, 8, 9):    # positions, pointToPixel, partition, boundary point types
+            assert np.array_equal(a.data[what], b.data[what]), bindings.GOF_NAMES[what]

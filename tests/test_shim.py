@@ -46,3 +46,13 @@ def test_gpu_shim_fills_reference_structures_like_the_reference(ra, shim):
     got, code = shim.encode_gof(frames, prm, occupancy_precision=2 if ra else 4)
     assert code == 0
     assert bindings.compare_gof(got, want) == []
+
+
+def test_decoder_side_binding_refuses_without_gpu(shim):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    frames = [synth.sphere(radius=10, center=40)]
+    prm = bindings.ctc_seg_params(bits=10, iterations=2, weight=(1.0, 1.0, 1.0))
+    got, code = shim.decode_gof(frames, prm)
+    assert code == -1   # PCCB200_ERR_NO_DEVICE from pccb200shim::decodeFrame: the reference stages ran, nothing was reconstructed on the CPU
