@@ -85,3 +85,15 @@ def test_gpu_decoder_side_binding_vs_reference():
     for a, b in zip(got, want):
         for what in (6, 7, 8, 9):    # positions, pointToPixel, partition, boundary point types
             assert np.array_equal(a.data[what], b.data[what]), bindings.GOF_NAMES[what]
+
+
+@pytest.mark.parametrize("kind", ["blob", "shell", "planes", "dust"])
+def test_gpu_product_vs_oracle_on_random_clouds(kind, oracle, product):
+    """the unstructured shapes of tests/test_oracle_fuzz.py with the product in place of the oracle (both packing modes)"""
+    from test_oracle_fuzz import cloud
+    rng = np.random.default_rng({"blob": 11, "shell": 12, "planes": 13, "dust": 14}[kind])
+    frames = [cloud(kind, rng), cloud(kind, rng)]
+    for ra, prec in ((0, 4), (1, 2)):
+        prm = bindings.ctc_seg_params(bits=10, iterations=6, weight=product.weight_normal(frames[0][0], 11))
+        prm.global_patch_allocation = ra
+        assert bindings.compare_gof(product.encode_gof(frames, prm, occupancy_precision=prec), oracle.encode_gof(frames, prm, occupancy_precision=prec)) == []
