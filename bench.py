@@ -2,6 +2,12 @@
 """bench.py — Mpoints/s of the V-PCC patch-generation + image-formation hot path (SURVEY.md §8a rows a1–a26).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--frames F] [--scale S]
+                  [--condition ai|ra] [--bits 10|11] [--ply-dir DIR]
+
+Workloads (BASELINE.json configs): default = configs[1] (longdress-like, 10 bit, 0.83 Mpts/frame, CTC all-intra r3, I=50);
+`--condition ra` = configs[2] (random-access r5: occupancyPrecision 2, global patch allocation); `--bits 11` = configs[4]
+(~2.9 Mpts/frame, 2560-wide canvas, I=20; use --frames 8 --gofs-in-flight 3: a frame keeps ~1.6 GB while in flight);
+`--ply-dir DIR` replaces the synthetic figure by real frames (e.g. longdress_vox10_1051..1082.ply) read by pccb200_ply_read.
 
 One "step" = one GOF (--frames F frames per GPU) of synthetic longdress-like frames (tests/synth.py `figure`, 10-bit, ≈0.83 M points
 per frame at the default scale) pushed through the whole hot path: generateSegments, placeSegments, occupancy / geometry
@@ -14,9 +20,10 @@ the orientation walk of a frame is a 1-2 s single-warp latency chain, so the GPU
 the other GOFs in flight. value / e2e are whole-job throughputs over the timed region (K GOFs, barrier to barrier).
 
 Multi-GPU (torchrun, one process per GPU): the frames of every GOF are sharded over the ranks (rank r takes F frames of
-an N*F-frame GOF: weak scaling); the one cross-frame coupling of the all-intra path — the common canvas size — is one
-NCCL all-reduce(MAX) of two integers between packing and image formation.  Timing: barrier + synchronize on both sides,
-max over ranks.
+an N*F-frame GOF: weak scaling); the one cross-frame coupling of the all-intra path — the common canvas size — is an
+NCCL all-reduce(MAX) issued by a comm thread on its own communicator / high-priority stream, several GOFs per collective, and
+taken off the critical path: image formation goes ahead on the local size and the reduced size is checked before the GOF is
+handed off (mpeg-pcc-tmc2_b200/sharding.py).  Timing: barrier + synchronize on both sides, max over ranks.
 
 JSON keys follow the driver contract.  value = throughput over the DEVICE window (first compute span to last span of any
 frame stream, CUDA events; input already uploaded), e2e = wall clock through the C ABI with host buffers including the
@@ -55,18 +62,43 @@ def pinned(shape, dtype):
 _PINNED = []
 
 
-def make_frames(count, scale, seed=0, distinct=8, pin=False):
+def read_ply_frames(directory, count):
+    """real frames: every .ply of the directory in name order through the product's own reader (PCCPointSet3::read semantics)"""
+    import ctypes as C
+    import bindings
+    lib = C.CDLL(bindings.PRODUCT_SO)
+    lib.pccb200_ply_read.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+    names = sorted(n for n in os.listdir(directory) if n.lower().endswith(".ply"))[:count]
+    if not names:
+        raise SystemExit("no .ply files in %s" % directory)
+    out = []
+    for nme in names:
+        path = os.path.join(directory, nme).encode()
+        n, col = C.c_size_t(0), C.c_int(0)
+        if lib.pccb200_ply_read(path, None, None, 0, C.byref(n), C.byref(col)) != 0:
+            raise SystemExit("cannot read %s" % nme)
+        xyz, rgb = np.zeros((n.value, 3), np.int16), np.zeros((n.value, 3), np.uint8)
+        if lib.pccb200_ply_read(path, xyz.ctypes.data_as(C.c_void_p), rgb.ctypes.data_as(C.c_void_p), n.value, C.byref(n), C.byref(col)) != 0:
+            raise SystemExit("cannot read %s" % nme)
+        out.append((xyz, rgb))
+    return out
+
+
+def make_frames(count, args, seed=0, distinct=8, pin=False):
     import synth
-    base = []
-    for f in range(min(count, distinct)):
-        xyz, rgb = synth.figure(scale=scale, seed=seed, frame=f)
+    if args.ply_dir:
+        base = read_ply_frames(args.ply_dir, count)
+    else:
+        base = [synth.figure(scale=args.scale, seed=seed, bits=args.bits, frame=f) for f in range(min(count, distinct))]
+    out = []
+    for xyz, rgb in base:
         xyz, rgb = np.ascontiguousarray(xyz), np.ascontiguousarray(rgb)
         if pin:
             px, pc = pinned(xyz.shape, xyz.dtype), pinned(rgb.shape, rgb.dtype)
             px[...], pc[...] = xyz, rgb
             xyz, rgb = px, pc
-        base.append((xyz, rgb))
-    return [base[f % len(base)] for f in range(count)]
+        out.append((xyz, rgb))
+    return [out[f % len(out)] for f in range(count)]
 
 
 class ClockSampler(threading.Thread):
@@ -118,27 +150,50 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# algorithmic bytes per launch of the single-kernel spans, N = points of the frame
+# Algorithmic bytes per frame of every stage span (every input streamed once, every output written once, a gather
+# counted as one pass over the gathered array). q: N source points, R reconstructed points, Q canvas pixels, I refine iterations,
+# prec occupancy precision. The refinement and patch-segmentation terms use §8d's worked-example model for the quantities the
+# kernels do not report (V = N/14 voxels, a quarter of them active with 64 adjacency entries, T = 4 outer iterations over
+# N, N/4, N/16, N/64 raw points, 60 smoothing passes over the push-pull pyramid): "model" in the roofline note.
 ALGO_BYTES = {
-    "knn16": lambda n: 6 * n + 64 * n,
-    "normals": lambda n: 64 * n + 6 * n + 24 * n,
-    "orient_walk": lambda n: 64 * n + 24 * n + 24 * n,
+    "kdtree_build": lambda q: 8 * q["N"] + 4 * q["N"] + 8 * q["N"] + 16 * (2 * q["N"] / 10),
+    "knn16": lambda q: 6 * q["N"] + 64 * q["N"],
+    "normals": lambda q: 64 * q["N"] + 6 * q["N"] + 24 * q["N"],
+    "orient": lambda q: 64 * q["N"] + 24 * q["N"] + 128 * q["N"],
+    "orient_walk": lambda q: 64 * q["N"] + 24 * q["N"] + 24 * q["N"],
+    "initial_seg": lambda q: 24 * q["N"] + q["N"],
+    "refine": lambda q: (7 * q["N"] + 12 * q["N"] / 14) + q["I"] * (12 * 0.25 * (q["N"] / 14) * 64 + 12 * q["N"] / 14 + 26 * 0.25 * q["N"]),
+    "patches": lambda q: 69 * 1.33 * q["N"] + 12 * q["N"] + 4 * q["R"] + 4 * (6 * q["N"] + 6 * q["R"] + 8 * q["N"]),
+    "images": lambda q: q["Q"] / q["prec"] ** 2 * 1.5 + 2 * q["Q"] * 1.5 + 2 * 2 * q["Q"] * 2,
+    "reconstruct": lambda q: q["Q"] / q["prec"] ** 2 + 4 * q["Q"] + 22 * q["R"],
+    "color_transfer": lambda q: (6 * q["R"] + 6 * q["N"] + 32 * q["R"]) + (6 * q["N"] + 6 * q["R"] + 4 * q["N"]) + 3 * q["N"] + 3 * q["R"],
+    "attribute_images": lambda q: 2 * q["Q"] * 3 + 2 * (4.0 / 3.0) * q["Q"] * 3 * (2 + 2 * 60),
 }
 
 
+def workload_name(args, npts):
+    cond = "all-intra r3 (occupancyPrecision 4)" if args.condition == "ai" else "random-access r5 (occupancyPrecision 2, global patch allocation)"
+    src = "real .ply frames from %s" % args.ply_dir if args.ply_dir else "synthetic longdress-like figure(scale=%.3f)" % args.scale
+    return "%s, %d-bit, %.2f Mpts/frame, CTC %s, I=%d refine iterations" % (src, args.bits, npts / 1e6, cond, args.iterations)
+
+
 def config(args, npts, frames_per_rank, world):
-    return {"workload": "synthetic longdress-like figure(scale=%.3f), 10-bit, %.2f Mpts/frame, %d frames/step/GPU (%d distinct), CTC all-intra r3 "
-                        "(occupancyPrecision 4, I=%d refine iterations)" % (args.scale, npts / 1e6, frames_per_rank, min(frames_per_rank, 8), args.iterations),
+    lanes = max(1, min(args.gofs_in_flight, args.steps))
+    sharded = args.condition == "ai"
+    return {"workload": workload_name(args, npts) + ", %d frames/step/GPU (%d distinct)" % (frames_per_rank, min(frames_per_rank, 8)),
             "stages": "a1-a26: kd-tree, k-NN16, PCA normals, spanning-tree orientation, initial + grid-refined segmentation, patch segmentation, "
                       "packing, occupancy/geometry images + dilation, generatePointCloud, colour transfer, attribute images, push-pull padding",
             "excluded": "ply load, videoEncoder.compress x3, post-processing, bitstream (as in BASELINE.md §4)",
-            "frames_in_flight": frames_per_rank * max(1, min(args.gofs_in_flight, args.steps)), "gofs_in_flight": max(1, min(args.gofs_in_flight, args.steps)), "host_cores": host_cores(), "parallelism": "frames of a GOF sharded over %d GPU(s)" % world,
+            "frames_in_flight": frames_per_rank * lanes, "gofs_in_flight": lanes, "host_cores": host_cores(),
+            "parallelism": ("frames of a GOF sharded over %d GPU(s), canvas size reduced by NCCL all-reduce(MAX), %d GOFs per collective, off the critical path"
+                            % (world, args.exchange_batch)) if sharded else "whole GOFs per GPU (%d GPU(s)), no collective on the data path" % world,
             "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2",
             "host_buffers": "pinned (inputs and the frames handed to the video codec)",
-            "handoff": "occupancy video + geometry D0/D1 luma + attribute T0/T1 converted to 8-bit YUV 4:2:0 on the device (the conversion the reference does inside compress())", "scratch_sets": args.scratch_sets}
+            "handoff": "occupancy video + geometry D0/D1 luma + attribute T0/T1 converted to 8-bit YUV 4:2:0 on the device (the conversion the reference does inside compress())",
+            "scratch_sets": args.scratch_sets}
 
 
-def run_reference(args, frames, prm):
+def run_reference(args, frames, prm, prec):
     """--impl reference: the reference's own CPU implementation (oracle/_ref, TBB off) on the host cores, one frame per process."""
     import multiprocessing as mp
     cores = max(1, min(len(frames), host_cores(), args.ref_frames))
@@ -147,7 +202,7 @@ def run_reference(args, frames, prm):
 
     def one(i):
         import bindings
-        bindings.Reference().encode_gof([work[i]], prm)
+        bindings.Reference().encode_gof([work[i]], prm, occupancy_precision=prec)
 
     def step():
         ps = [ctx.Process(target=one, args=(i,)) for i in range(cores)]
@@ -168,10 +223,52 @@ def run_reference(args, frames, prm):
     cfg["note"] = "reference TMC2 v24.0 compiled from /root/reference (ENABLE_TBB off, CTC --nbThread=1), one frame per host process"
     return {"metric": METRIC, "value": val, "unit": "Mpoints/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps_ref,
             "warmup": args.warmup_ref, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int16/f64", "data": "synthetic", "config": cfg,
+            "dtype": "int16/f64", "data": "real" if args.ply_dir else "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": "Mpoints/s", "cores": cores, "kind": "reference",
                              "sample": "%d frame(s) of the workload per step, one per host core (%d timed step(s) after %d warm-up)" % (cores, args.steps_ref, args.warmup_ref)},
             "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def build_params(args, weight):
+    import bindings
+    prm = bindings.ctc_seg_params(bits=args.bits, iterations=args.iterations, weight=weight)
+    if args.condition == "ra":
+        prm.global_patch_allocation = 1   # cfg/condition/ctc-random-access.cfg (constrainedPack stays at its default 1)
+    return prm
+
+
+def parity_check(prod, frame0, prm, prec, handoff_of_last_gof):
+    """frame 0 of the workload through the CUDA path against the reference's own CPU run of the same frame (oracle/_ref), every
+    product; without the compiled reference, against the reference-generated digests of tests/golden/gof_fullsize.json.
+    Returns (cpu seconds or None, dict for the JSON line)."""
+    import bindings
+    got = prod.encode_gof([frame0], prm, occupancy_precision=prec)
+    info = {"parity_checked": False}
+    sec = None
+    if os.path.exists(bindings.REF_SO):
+        ref = bindings.Reference()
+        t0 = time.perf_counter()
+        want, _ = ref.encode_gof([frame0], prm, occupancy_precision=prec)
+        sec = time.perf_counter() - t0
+        bad = bindings.compare_gof(got, want)
+        info = {"parity_checked": True, "parity_ok": bad == [], "parity_against": "oracle/_ref (the compiled reference) on frame 0 of the workload: "
+                "patch list + depth/occupancy arenas + all 16 products (a13-a26, YUV hand-off), bit-exact", "parity_mismatches": bad[:6]}
+    else:
+        import hashlib
+        path = os.path.join(ROOT, "tests", "golden", "gof_fullsize.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                gold = json.load(f)["cases"]
+            key = {("ai", 10): "ai_r3", ("ra", 10): "ra_r5", ("ai", 11): "vox11"}.get((prm.global_patch_allocation and "ra" or "ai", prm.geometry_bitdepth_3d - 1))
+            if key in gold and gold[key]["points"][0] == len(frame0[0]) and (got[0].width, got[0].height) == (gold[key]["frames"][0]["width"], gold[key]["frames"][0]["height"]) and key != "ra_r5":
+                g0 = gold[key]["frames"][0]
+                bad = [n for w, n in bindings.GOF_NAMES.items() if hashlib.sha256(np.ascontiguousarray(got[0].data[w]).tobytes()).hexdigest() != g0[n]]
+                info = {"parity_checked": True, "parity_ok": bad == [], "parity_against": "tests/golden/gof_fullsize.json (sha256 of the reference's products, frame 0)", "parity_mismatches": bad[:6]}
+    # the frames the TIMED pipeline handed off are the ones just checked (same frame, same canvas)
+    if handoff_of_last_gof is not None and info.get("parity_checked"):
+        same = all(np.array_equal(buf, got[0].data[what]) for what, buf in handoff_of_last_gof.items() if buf.size == got[0].data[what].size)
+        info["timed_handoff_matches_checked_frame"] = bool(same)
+    return sec, info
 
 
 def main():
@@ -181,14 +278,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frames per step and GPU (a GOF is 32 frames)")
-    ap.add_argument("--scale", type=float, default=0.626, help="figure scale; 0.626 gives ~0.83 Mpts/frame like longdress_vox10")
-    ap.add_argument("--iterations", type=int, default=50, help="iterationCountRefineSegmentation (longdress cfg: 50)")
+    ap.add_argument("--scale", type=float, default=None, help="figure scale; default 0.626 (10 bit: ~0.83 Mpts/frame like longdress_vox10) / 0.585 (11 bit: ~2.9 Mpts)")
+    ap.add_argument("--bits", type=int, default=10, choices=[10, 11], help="geometry3dCoordinatesBitdepth (11: basketball_player_vox11, 2560-wide canvas)")
+    ap.add_argument("--condition", default="ai", choices=["ai", "ra"], help="ai: CTC all-intra r3 (BASELINE configs[1]); ra: CTC random-access r5 (configs[2])")
+    ap.add_argument("--iterations", type=int, default=None, help="iterationCountRefineSegmentation (longdress cfg: 50; basketball_player: 20)")
+    ap.add_argument("--ply-dir", default=None, help="directory of .ply frames (sorted by name) to use instead of the synthetic figure; read by pccb200_ply_read")
     ap.add_argument("--ref-frames", type=int, default=32, help="frames per step of the reference arm (one host process per frame, up to the core count)")
     ap.add_argument("--gofs-in-flight", type=int, default=8, help="GOFs processed concurrently (each on its own context); steps are independent GOFs")
+    ap.add_argument("--exchange-batch", type=int, default=4, help="GOFs whose canvas sizes share one all-reduce (multi-GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timeline", default=None, help="write the last GOF's per-frame stage spans (name, start ms, ms) to this JSON file")
     ap.add_argument("--scratch-sets", type=int, default=24, help="scratch sets of the device pool = frames inside the data-parallel stage groups at once")
     args = ap.parse_args()
+    if args.scale is None:
+        args.scale = 0.626 if args.bits == 10 else 0.585
+    if args.iterations is None:
+        args.iterations = 50 if args.bits == 10 else 20
+    prec = 4 if args.condition == "ai" else 2
     # reference arm: every step is a bounded sample (one frame per host core, ~15 s); a few steps keep the run within minutes
     args.steps_ref, args.warmup_ref = max(1, min(args.steps, 3)), min(args.warmup, 1)
 
@@ -199,31 +305,38 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            frames = make_frames(min(args.frames, args.ref_frames), args.scale, seed=0)
-            weight = tuple(bindings.Reference().weight_normal(frames[0][0], 11))
-            print(json.dumps(run_reference(args, frames, bindings.ctc_seg_params(bits=10, iterations=args.iterations, weight=weight))))
+            frames = make_frames(min(args.frames, args.ref_frames), args, seed=0)
+            weight = tuple(bindings.Reference().weight_normal(frames[0][0], args.bits + 1))
+            print(json.dumps(run_reference(args, frames, build_params(args, weight), prec)))
         return
 
     import torch
     dist = None
     real_stdout = os.dup(1)
     os.dup2(2, 1)   # NCCL / library chatter must not precede the JSON line on stdout: everything but the result goes to stderr
+    exchange_group = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
-    frames = make_frames(args.frames, args.scale, seed=rank, pin=True)
+        if args.condition == "ai":   # the canvas exchange gets its own communicator + high-priority stream
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            exchange_group = dist.new_group(backend="nccl", pg_options=opts)
+    sharded = world > 1 and args.condition == "ai"
+    sys.path.insert(0, os.path.join(ROOT, "mpeg-pcc-tmc2_b200"))
+    from sharding import CanvasExchange
+    frames = make_frames(args.frames, args, seed=rank, pin=True)
     lanes = max(1, min(args.gofs_in_flight, args.steps))          # GOFs in flight: one library context (streams + buffers) each
     prods = [bindings.Product(local) for _ in range(lanes)]
     prod = prods[0]
     prod.lib.pccb200_set_scratch_sets(local, args.scratch_sets)
     # axis weights come from frame 0 of the GOF (rank 0's first frame); every rank needs the same three doubles
-    w = torch.tensor(prod.weight_normal(frames[0][0], 11), dtype=torch.float64)
-    if dist is not None:
+    w = torch.tensor(prod.weight_normal(frames[0][0], args.bits + 1), dtype=torch.float64)
+    if sharded:
         wd = w.cuda()
         dist.broadcast(wd, 0)
         w = wd.cpu()
-    prm = bindings.ctc_seg_params(bits=10, iterations=args.iterations, weight=tuple(float(x) for x in w))
+    prm = build_params(args, tuple(float(x) for x in w))
     for p in prods:
         p.profile(True)
     total_pts = sum(len(f[0]) for f in frames)
@@ -231,14 +344,10 @@ def main():
 
     def phase_a(lane):
         """a1..a13 of one GOF: segmentation (incl. the orientation walk) + packing"""
-        t0 = time.perf_counter()
-        g = bindings.ProductGof(prods[lane], frames, prm, 4)
-        return g, (t0, time.perf_counter())
+        return bindings.ProductGof(prods[lane], frames, prm, prec)
 
-    def phase_b(lane, g, t0, W, H):
+    def phase_b(g, W, H):
         """a16..a26 + hand-off: images, reconstruction, colour, attribute images; D2H of every frame the codec would receive"""
-        p = prods[lane]
-        t0, ta = t0
         g.resume(W, H, 0)
         t1 = time.perf_counter()
         nbytes = 0
@@ -250,15 +359,11 @@ def main():
                         outbuf[(f, what)] = pinned((cnt,), bindings.GOF_DTYPES[what])
                     g.fetch(f, what, outbuf[(f, what)])
                     nbytes += outbuf[(f, what)].nbytes
-        t2 = time.perf_counter()
-        spans = p.profile_read()
-        g.free()
-        host_phases.append((ta - t0, t1 - ta, t2 - t1, time.perf_counter() - t0))
-        gof_log.append((lane, t0, ta, t1, t2, time.perf_counter()))
-        return t1 - t0, t2 - t0, spans, nbytes
+        return t1, time.perf_counter(), nbytes
 
-    gof_log = []       # per GOF: lane, absolute times of start / packed / resumed / fetched / freed
-    host_phases = []   # per GOF: seconds in encode_gof(stop_after=1), all-reduce + resume, fetch, whole lane cycle
+    gof_log = []       # per GOF: lane, absolute times of start / packed / resumed / fetched / verified / freed
+    host_phases = []   # per GOF: seconds in segment_and_pack, image formation, fetch, wait for the reduced canvas size, whole cycle
+    stats = {"reformed": 0}
 
     def in_threads(fn, count):
         out = [None] * count
@@ -275,11 +380,13 @@ def main():
         """`count` independent GOFs. One lane: strictly one after the other. Several lanes: a software pipeline - every lane (own
         library context: streams + buffers) takes the next GOF as soon as it has finished its previous one, the lanes start
         staggered, so that one GOF's orientation walks (32 resident warps, GPU otherwise idle) overlap the data-parallel stages of
-        the others. Per GOF: phase A, ONE all-reduce(MAX) of the canvas size (multi-GPU only, issued in GOF order on every rank),
-        phase B."""
+        the others. Per GOF: phase A; the canvas size is posted to the exchange (multi-GPU: one NCCL all-reduce(MAX) per
+        `--exchange-batch` GOFs, issued by the comm thread in GOF order); phase B goes ahead on the local size and the reduced size
+        is checked before the GOF counts as done (re-formed on the larger canvas if another rank needed more rows)."""
         results = [None] * count
-        lock = threading.Condition()
-        state = {"next": 0, "turn": 0}
+        lock = threading.Lock()
+        state = {"next": 0}
+        ex = CanvasExchange(dist, count, batch=args.exchange_batch, group=exchange_group, device=local) if sharded else None
 
         def worker(lane):
             torch.cuda.set_device(local)   # (the current device is per thread)
@@ -291,39 +398,52 @@ def main():
                     state["next"] += 1
                 if g >= count:
                     return
-                gof, t0 = phase_a(lane)
+                t0 = time.perf_counter()
+                gof = phase_a(lane)
+                ta = time.perf_counter()
                 W, H = gof.dims(0)[:2]
-                if dist is not None:  # the one collective: common canvas size of the GOF across the ranks holding its frames
-                    with lock:
-                        while state["turn"] != g:
-                            lock.wait()
-                    wh = torch.tensor([W, H], device="cuda", dtype=torch.int64)
-                    dist.all_reduce(wh, op=dist.ReduceOp.MAX)
-                    W, H = (int(x) for x in wh.cpu())
-                    with lock:
-                        state["turn"] += 1
-                        lock.notify_all()
-                results[g] = phase_b(lane, gof, t0, W, H)
+                if ex is not None:
+                    ex.post(g, W, H)
+                t1, t2, nbytes = phase_b(gof, W, H)
+                tv = t2
+                if ex is not None:
+                    Wg, Hg = ex.wait(g)
+                    tv = time.perf_counter()
+                    if (Wg, Hg) != (W, H):   # another rank's frames needed a larger canvas: form this GOF again on it
+                        stats["reformed"] += 1
+                        _, _, nbytes = phase_b(gof, Wg, Hg)
+                spans = prods[lane].profile_read()
+                gof.free()
+                tf = time.perf_counter()
+                host_phases.append((ta - t0, t1 - ta, t2 - t1, tv - t2, tf - t0))
+                gof_log.append((lane, t0, ta, t1, t2, tv, tf))
+                results[g] = (t1 - t0, t2 - t0, spans, nbytes)
 
         in_threads(worker, min(lanes, count))
-        return results
+        xs = None
+        if ex is not None:
+            ex.close()
+            xs = (ex.collectives, ex.seconds)
+        return results, xs
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    warm = max(args.warmup, 2 * lanes)   # every context (lane) allocates its buffers in its first GOF; its second one runs warm
-    wres = run_steps(warm)
+    # initialisation (untimed, not a warm-up step): every lane's context allocates its buffers while processing its first GOF
+    ires, _ = run_steps(lanes)
+    wres, _ = run_steps(args.warmup) if args.warmup > 0 else ([], None)
     if lanes > 1:   # steady-state spacing of GOF starts: latency of one (warm) GOF / lanes
-        stagger[0] = float(np.min([e for _, e, _, _ in wres])) / lanes
+        stagger[0] = float(np.min([e for _, e, _, _ in (wres or ires)])) / lanes
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     del host_phases[:]
     del gof_log[:]
+    stats["reformed"] = 0
     t_begin = time.perf_counter()
-    res = run_steps(args.steps)
+    res, xstats = run_steps(args.steps)
     barrier()
     wall_total = time.perf_counter() - t_begin
     clocks = sampler.finish()
@@ -352,45 +472,67 @@ def main():
     for nme, ms, st in last_spans:
         agg.setdefault(nme, []).append(ms)
     mean_ms = {k: float(np.mean(v)) for k, v in agg.items()}
-    dom = max((k for k in mean_ms if k in ALGO_BYTES), key=lambda k: mean_ms[k])
     peak, how = measured_peak()
     npts = float(np.mean([len(f[0]) for f in frames]))
-    per_launch = args.frames if dom == "orient_walk" else 1   # the walks of all frames of a GOF share one launch
-    algo_bytes = ALGO_BYTES[dom](npts) * per_launch
+    # sizes of the last GOF for the algorithmic-bytes formulas
+    g = bindings.ProductGof(prod, frames[:1], prm, prec)
+    W, H = g.dims(0)[:2]
+    g.resume(W, H, 0)
+    R = g.dims(0)[2]
+    g.free()
+    prod.profile_read()
+    q = {"N": npts, "R": float(R), "Q": float(W * H), "I": float(args.iterations), "prec": float(prec)}
+    # a span's duration is per frame, except the walk: all frames of a GOF walk in ONE launch (one CTA each)
+    per_launch = {k: (args.frames if k == "orient_walk" else 1) for k in ALGO_BYTES}
+    table = {}
+    for k, fn in ALGO_BYTES.items():
+        if k in mean_ms and mean_ms[k] > 0:
+            b = fn(q) * per_launch[k]
+            table[k] = {"ms": round(mean_ms[k], 3), "algorithmic_bytes": int(b), "achieved_gbs": round(b / (mean_ms[k] * 1e-3) / 1e9, 3),
+                        "frac": b / (mean_ms[k] * 1e-3) / 1e9 / peak}
+    dom = max(table, key=lambda k: table[k]["ms"])
+    algo_bytes = table[dom]["algorithmic_bytes"]
     ach = algo_bytes / (mean_ms[dom] * 1e-3) / 1e9
+    path_bytes = sum(fn(q) for fn in ALGO_BYTES.values())                       # per frame, whole hot path
+    path_gbs = path_bytes * (pts_all / npts) / dev_t / 1e9                        # frames processed / device time
     h2d = sum(f[0].nbytes + f[1].nbytes for f in frames)
     out = {
-        "metric": METRIC, "value": pts_all / dev_t / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-        "ms_per_step": wall_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int16/f64", "data": "synthetic", "config": config(args, npts, args.frames, world),
+        "metric": METRIC, "value": pts_all / dev_t / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "init_gofs": lanes, "ms_per_step": wall_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16/f64", "data": "real" if args.ply_dir else "synthetic", "config": config(args, npts, args.frames, world),
         "e2e": {"value": pts_all / e2e_t / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": None,
         "stage_ms_per_frame": {k: round(v, 3) for k, v in sorted(mean_ms.items(), key=lambda kv: -kv[1])},
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "peak_source": how, "algorithmic_bytes_per_launch": algo_bytes,
-                     "note": "sequential spanning-tree walk, one warp per frame, all frames of a GOF in one launch: latency-bound by construction"},
+                     "note": "dominant stage span of the last timed GOF (spans overlap the other GOFs in flight, so durations are under load); "
+                             "refine / patches / attribute_images bytes use the SURVEY 8d model constants",
+                     "per_stage": table,
+                     "whole_path": {"algorithmic_bytes_per_frame": int(path_bytes), "achieved_gbs": round(path_gbs, 2), "frac": path_gbs / peak / max(1, world)}},
         "clocks": clocks,
         "gof_device_window_ms": [round(x * 1e3, 1) for x in dev_each],
         "gof_log_ms": [[g[0]] + [round((x - t_begin) * 1e3) for x in g[1:]] for g in sorted(gof_log, key=lambda g: g[1])],
-        "host_ms_per_gof": dict(zip(("segment_and_pack", "resume", "fetch", "cycle"), (round(float(np.median(c)) * 1e3, 1) for c in zip(*host_phases)))),
+        "host_ms_per_gof": dict(zip(("segment_and_pack", "form_images", "fetch", "canvas_wait", "cycle"), (round(float(np.median(c)) * 1e3, 1) for c in zip(*host_phases)))),
         "gpu_mem_used_gb": round((torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 2**30, 1),
     }
+    if xstats is not None:
+        out["canvas_exchange"] = {"collectives": xstats[0], "ms_per_collective": round(xstats[1] / max(1, xstats[0]) * 1e3, 2), "gofs_reformed": stats["reformed"]}
     counts_path = os.path.join(ROOT, "profiles", "launch_counts.json")
     if os.path.exists(counts_path):
         with open(counts_path) as f:
             lc = json.load(f)
         out["gpu_launches"] = int(lc.get("launches_per_frame", 0) * args.frames * args.steps)
         out["gpu_launches_source"] = lc.get("source")
-        if lc.get("traffic_bytes_per_frame", {}).get(dom):   # ncu --set full of the kernel on ONE frame; a launch covers per_launch frames
-            out["roofline"]["traffic"] = int(lc["traffic_bytes_per_frame"][dom] * per_launch)
+        if lc.get("traffic_bytes_per_frame", {}).get(dom):   # ncu dram bytes of the stage's kernels on ONE frame; a launch covers per_launch frames
+            out["roofline"]["traffic"] = int(lc["traffic_bytes_per_frame"][dom] * per_launch[dom])
             out["roofline"]["traffic_source"] = lc.get("traffic_source")
-    if not args.no_cpu_baseline and os.path.exists(bindings.REF_SO):
-        ref = bindings.Reference()
-        t0 = time.perf_counter()
-        ref.encode_gof([frames[0]], prm)
-        sec = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": len(frames[0][0]) / sec / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "reference",
-                               "sample": "1 frame of the workload (%.2f Mpts) through the reference's own stages, single thread (CTC --nbThread=1)" % (len(frames[0][0]) / 1e6)}
+    if not args.no_cpu_baseline:
+        last = {what: outbuf[(0, what)] for what in HANDOFF if (0, what) in outbuf} if args.frames > 0 else None
+        sec, info = parity_check(prod, frames[0], prm, prec, last)
+        out.update(info)
+        if sec is not None:
+            out["cpu_baseline"] = {"value": len(frames[0][0]) / sec / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "reference",
+                                   "sample": "1 frame of the workload (%.2f Mpts) through the reference's own stages, single thread (CTC --nbThread=1)" % (len(frames[0][0]) / 1e6)}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(out), flush=True)

@@ -163,7 +163,9 @@ int  pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xy
                          const pccb200_seg_params* params, int occupancy_precision, int stop_after, pccb200_gof** out );
 /* Multi-GPU (frames of one GOF sharded over ranks): call pccb200_encode_gof with stop_after = 1 on every rank, all-reduce
  * (MAX) the canvas size from pccb200_gof_dims — the one cross-frame reduction of the all-intra path
- * (PCCEncoder::resizeGeometryVideo, PCCEncoder.cpp:5546-5591) — then resume the remaining stages on that canvas. */
+ * (PCCEncoder::resizeGeometryVideo, PCCEncoder.cpp:5546-5591) — then resume the remaining stages on that canvas.
+ * A rank need not wait for the reduction: it may resume on its local size at once and, should the reduced size turn out larger,
+ * call pccb200_gof_resume( gof, W, H, 0 ) again on the finished GOF with the larger canvas (all products are formed anew). */
 int  pccb200_gof_resume( pccb200_gof* gof, size_t width, size_t height, int stop_after );
 /* Lossy geometry codec: run pccb200_encode_gof / pccb200_gof_resume with stop_after = 2, hand GOF_OM_VIDEO / GOF_GEO0 / GOF_GEO1 to
  * the codec, give the DECODED luma planes back (any pointer may be NULL = keep the source), then pccb200_gof_resume(gof, W, H, 0)

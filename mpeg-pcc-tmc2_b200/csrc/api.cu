@@ -168,9 +168,7 @@ int pccb200_segment_frame( pccb200_ctx* ctx, const int16_t* xyz, const uint8_t* 
                            double* normals, uint8_t* part0, uint8_t* part1, pccb200_patchlist** out ) {
   return guarded( ctx, [&]() -> int {
     if ( !xyz || !rgb || !prm || !out ) return PCCB200_ERR_BAD_ARG;
-    if ( prm->nn_normal_estimation != 16 || prm->max_nn_count_patch_seg != 16 || prm->geometry_bitdepth_3d > 12 ||
-         ( prm->normal_orientation != 0 && prm->normal_orientation != 1 ) )
-      return PCCB200_ERR_UNSUPPORTED;
+    if ( !segParamsSupported( *prm ) ) return PCCB200_ERR_UNSUPPORTED;
     *out = nullptr;
     pccb200_patchlist* pl = new pccb200_patchlist();
     if ( n == 0 ) {

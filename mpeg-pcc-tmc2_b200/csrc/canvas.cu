@@ -162,7 +162,7 @@ __global__ void kBlockToPatch( const CanvasPatch* __restrict__ patches, const ui
   int       bx, by;
   blockToCanvas( m, ub, vb, bx, by );
   const int bw = W / occRes, ow = W / prec, cells = occRes / prec;
-  if ( bx >= bw || by >= H / occRes ) return;
+  if ( bx < 0 || by < 0 || bx >= bw || by >= H / occRes ) return;
   bool any = false;
   for ( int j = 0; j < cells && !any; ++j )
     for ( int i = 0; i < cells && !any; ++i ) any = om[size_t( by * cells + j ) * ow + bx * cells + i] != 0;
@@ -256,7 +256,7 @@ __device__ __forceinline__ int reconstructElement( const CanvasPatch& m, int pat
   const int ub = blk % m.sizeU0, vb = blk / m.sizeU0;
   int       bx, by;
   blockToCanvas( m, ub, vb, bx, by );
-  if ( bx >= W / occRes || by >= H / occRes ) return 0;
+  if ( bx < 0 || by < 0 || bx >= W / occRes || by >= H / occRes ) return 0;
   if ( blockToPatch[size_t( by ) * ( W / occRes ) + bx] != uint32_t( patchIndex ) + 1u ) return 0;
   const int u = ub * occRes + pix % occRes, v = vb * occRes + pix / occRes;
   pixelToCanvas( m, occRes, u, v, x, y );

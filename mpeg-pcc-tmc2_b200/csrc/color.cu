@@ -9,10 +9,13 @@
 //      nanoflann result order (a coinciding source point wins outright).
 // Both neighbour searches run on nanoflann-identical trees (kdtree.cu), so ties resolve as in the reference.
 // Votes are grouped per target with one stable radix sort on (target, distance) — equal distances keep ascending source
-// order, which is what the reference's insertion sort (std::sort on <= 16 elements) produces.
+// order, which is what the reference's insertion sort (std::sort on <= 16 elements) produces. A target with MORE than 16 votes
+// goes through libstdc++'s introsort in the reference (PCCPointSet.cpp:955), which permutes ties: those runs are re-ordered by
+// the step-by-step emulation of stdsort.cuh before the fp64 accumulation, so the sums stay bit-exact for any run length.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "stages.cuh"
+#include "stdsort.cuh"
 
 namespace pccb200 {
 
@@ -50,35 +53,63 @@ __global__ void __launch_bounds__( 128 )
   out[i] = make_uchar4( roundClip( a0 / sw ), roundClip( a1 / sw ), roundClip( a2 / sw ), 0 );
 }
 
+constexpr int      kDistBits = 26;
+constexpr uint32_t kDistMask = ( 1u << kDistBits ) - 1u;
+struct VoteLessByDistance {  // the reference's comparator: distance only (ties are where std::sort's algorithm shows)
+  __host__ __device__ bool operator()( const uint64_t& a, const uint64_t& b ) const { return ( a >> 32 ) < ( b >> 32 ); }
+};
+
 __global__ void kVoteKeys( const uint32_t* __restrict__ target, const float* __restrict__ dist, int n, uint64_t* __restrict__ keys,
                            uint32_t* __restrict__ ids ) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if ( s >= n ) return;
-  keys[s] = ( uint64_t( target[s] ) << 24 ) | uint64_t( uint32_t( dist[s] ) & 0xFFFFFFu );
+  // squared distances are exact integers below 2^26 (12-bit coordinates: 3 * 4095^2)
+  keys[s] = ( uint64_t( target[s] ) << kDistBits ) | uint64_t( uint32_t( dist[s] ) & kDistMask );
   ids[s]  = s;
 }
 
-// one thread per vote position; the head of each target's run accumulates the whole run in order
+// one thread per vote position; the head of each target's run accumulates the whole run in order.
+// `scratch` (the radix sort's input keys, dead after the sort) gives a run of more than 16 votes a private work area at its own
+// positions [p, e): the votes are put back into arrival order (ascending source index, as the reference pushes them) and sorted
+// by the std::sort emulation.
 __global__ void __launch_bounds__( 128 )
     kBackward( const uint64_t* __restrict__ keys, const uint32_t* __restrict__ srcIds, int n, const uchar4* __restrict__ srcRgb,
-               uchar4* __restrict__ recRgb ) {
+               uchar4* __restrict__ recRgb, uint64_t* __restrict__ scratch ) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if ( p >= n ) return;
-  const uint32_t tgt = uint32_t( keys[p] >> 24 );
-  if ( p > 0 && uint32_t( keys[p - 1] >> 24 ) == tgt ) return;
+  const uint32_t tgt = uint32_t( keys[p] >> kDistBits );
+  if ( p > 0 && uint32_t( keys[p - 1] >> kDistBits ) == tgt ) return;
   int e = p + 1;
-  while ( e < n && uint32_t( keys[e] >> 24 ) == tgt ) ++e;
+  while ( e < n && uint32_t( keys[e] >> kDistBits ) == tgt ) ++e;
   const uchar4 first = srcRgb[srcIds[p]];
-  if ( ( keys[p] & 0xFFFFFFu ) == 0 || e - p == 1 ) {
+  if ( ( keys[p] & kDistMask ) == 0 || e - p == 1 ) {
     recRgb[tgt] = first;  // a source point at this very position, or a single vote: round(1.0 * c) == c
     return;
   }
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, sw = 0.0;
-  for ( int j = p; j < e; ++j ) {
-    const double w = 1 / ( sqrt( double( uint32_t( keys[j] & 0xFFFFFFu ) ) ) + 4.0 );
-    const uchar4 c = srcRgb[srcIds[j]];
-    a0 += ( double( c.x ) * w ), a1 += ( double( c.y ) * w ), a2 += ( double( c.z ) * w );
-    sw += w;
+  if ( e - p <= 16 ) {
+    for ( int j = p; j < e; ++j ) {
+      const double w = 1 / ( sqrt( double( uint32_t( keys[j] & kDistMask ) ) ) + 4.0 );
+      const uchar4 c = srcRgb[srcIds[j]];
+      a0 += ( double( c.x ) * w ), a1 += ( double( c.y ) * w ), a2 += ( double( c.z ) * w );
+      sw += w;
+    }
+  } else {
+    uint64_t* v   = scratch + p;
+    const int len = e - p;
+    for ( int j = 0; j < len; ++j ) {  // (distance << 32 | source index), inserted in ascending source index
+      const uint64_t item = ( uint64_t( uint32_t( keys[p + j] & kDistMask ) ) << 32 ) | srcIds[p + j];
+      int            b    = j;
+      while ( b > 0 && uint32_t( v[b - 1] ) > uint32_t( item ) ) v[b] = v[b - 1], --b;
+      v[b] = item;
+    }
+    stdsort::sort( v, v + len, VoteLessByDistance() );
+    for ( int j = 0; j < len; ++j ) {
+      const double w = 1 / ( sqrt( double( uint32_t( v[j] >> 32 ) ) ) + 4.0 );
+      const uchar4 c = srcRgb[uint32_t( v[j] )];
+      a0 += ( double( c.x ) * w ), a1 += ( double( c.y ) * w ), a2 += ( double( c.z ) * w );
+      sw += w;
+    }
   }
   // color0 = clip( round( w*centroid1 + (1-w)*centroid2 ) ) with w = 0
   recRgb[tgt] = make_uchar4( roundClip( 0.0 * 0.0 + 1.0 * ( a0 / sw ) ), roundClip( 0.0 * 0.0 + 1.0 * ( a1 / sw ) ),
@@ -102,10 +133,10 @@ void transferColors( ColorScratch& sc, const KdTree& srcTree, const short4* srcP
   int tbits = 1;
   while ( ( size_t( 1 ) << tbits ) < R ) ++tbits;
   size_t tmpBytes = 0;
-  PCC_CUDA( cub::DeviceRadixSort::SortPairs( nullptr, tmpBytes, sc.keysA.p, sc.keysB.p, sc.idsA.p, sc.idsB.p, int( n ), 0, 24 + tbits, s ) );
+  PCC_CUDA( cub::DeviceRadixSort::SortPairs( nullptr, tmpBytes, sc.keysA.p, sc.keysB.p, sc.idsA.p, sc.idsB.p, int( n ), 0, kDistBits + tbits, s ) );
   sc.cubTmp.reserve( tmpBytes + 16 );
-  PCC_CUDA( cub::DeviceRadixSort::SortPairs( sc.cubTmp.p, tmpBytes, sc.keysA.p, sc.keysB.p, sc.idsA.p, sc.idsB.p, int( n ), 0, 24 + tbits, s ) );
-  kBackward<<<divUp( n, 128 ), 128, 0, s>>>( sc.keysB, sc.idsB, int( n ), srcRgb, recRgb );
+  PCC_CUDA( cub::DeviceRadixSort::SortPairs( sc.cubTmp.p, tmpBytes, sc.keysA.p, sc.keysB.p, sc.idsA.p, sc.idsB.p, int( n ), 0, kDistBits + tbits, s ) );
+  kBackward<<<divUp( n, 128 ), 128, 0, s>>>( sc.keysB, sc.idsB, int( n ), srcRgb, recRgb, sc.keysA );
   PCC_LAUNCH_CHECK();
 }
 

@@ -105,6 +105,17 @@ struct ScratchLease {
   ScratchLease& operator=( const ScratchLease& ) = delete;
 };
 
+// Parameter combinations the CUDA path implements (the CTC values and the variations the tests cover). Anything
+// else is PCCB200_ERR_UNSUPPORTED at the entry point - never a silently different result.
+//  * voxel_dim_refine: only 4. Dimensions 1 / 2 make the reference classify edge voxels over a 5x5x5 neighbourhood
+//    (idvSearchRange 2, PCCPatchSegmenter.cpp:1470: up to 125 near voxels); refine.cu keeps 27 (the 3x3x3 of dimension >= 4).
+//  * search_radius_refine: the lattice offsets with d^2 < (radius >> 2) must fit the adjacency kernel's hit buffer (2048).
+inline bool segParamsSupported( const pccb200_seg_params& p ) {
+  return p.nn_normal_estimation == 16 && p.max_nn_count_patch_seg == 16 && p.geometry_bitdepth_3d >= 1 && p.geometry_bitdepth_3d <= 12 &&
+         ( p.normal_orientation == 0 || p.normal_orientation == 1 ) && p.voxel_dim_refine == 4 && p.search_radius_refine >= 4 &&
+         ( p.search_radius_refine >> 2 ) <= 56 && p.max_nn_count_refine >= 1 && p.iteration_count_refine >= 0;
+}
+
 template <class F>
 inline int guarded( pccb200_ctx* ctx, F&& f ) {
   if ( !ctx ) return PCCB200_ERR_BAD_ARG;

@@ -88,6 +88,10 @@ struct WalkGate {
         snprintf( buf, sizeof( buf ), "orientation walk: CUDA error %d (%s) at %s:%d", int( e.code ), cudaGetErrorString( e.code ), e.file, e.line );
         failed = true, error = buf;
         cudaGetLastError();
+      } catch ( const std::exception& e ) {  // (e.g. bad_alloc: the other frame threads must still be released)
+        failed = true, error = std::string( "orientation walk: " ) + e.what();
+      } catch ( ... ) {
+        failed = true, error = "orientation walk: unknown failure";
       }
       done = true;
       cv.notify_all();
@@ -104,6 +108,7 @@ void segmentFrameBeforeWalk( FrameState& fs, const pccb200_seg_params& prm ) {
   Profiler*    pf = &fs.prof;
   fs.seg.patches.clear();
   fs.seg.depthElems = fs.seg.occElems = 0;
+  fs.orient.walkSmem = 0;  // (frame states are pooled: an empty frame must not re-submit the previous GOF's walk)
   if ( n == 0 ) return;
   {
     ProfScope t( pf, "h2d", s );
@@ -126,7 +131,6 @@ void segmentFrameBeforeWalk( FrameState& fs, const pccb200_seg_params& prm ) {
     ProfScope t( pf, "normals", s );
     computeNormals( fs.xyz4, fs.nbr, k, n, fs.normals, s );
   }
-  fs.orient.walkSmem = 0;
   if ( prm.normal_orientation == 1 ) {
     ProfScope t( pf, "orient", s );
     fs.orient.prof = pf;
@@ -356,8 +360,7 @@ extern "C" {
 int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
                         const pccb200_seg_params* prm, int occupancyPrecision, int stopAfter, pccb200_gof** out ) {
   if ( !ctx || !out || nframes < 0 || ( nframes > 0 && ( !xyz || !rgb || !n ) ) || !prm ) return PCCB200_ERR_BAD_ARG;
-  if ( prm->nn_normal_estimation != 16 || prm->max_nn_count_patch_seg != 16 || prm->geometry_bitdepth_3d > 12 || prm->occupancy_resolution != 16 ||
-       ( prm->normal_orientation != 0 && prm->normal_orientation != 1 ) || occupancyPrecision < 1 || 16 % occupancyPrecision != 0 ||
+  if ( !segParamsSupported( *prm ) || prm->occupancy_resolution != 16 || occupancyPrecision < 1 || 16 % occupancyPrecision != 0 ||
        prm->map_count_minus1 != 1 || ( prm->global_patch_allocation != 0 && prm->global_patch_allocation != 1 ) )
     return PCCB200_ERR_UNSUPPORTED;
   *out = nullptr;
@@ -468,6 +471,13 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
 
 int pccb200_gof_resume( pccb200_gof* g, size_t width, size_t height, int stopAfter ) {
   if ( !g || stopAfter == 1 ) return PCCB200_ERR_BAD_ARG;
+  // A finished GOF (stage 4) may be formed AGAIN on a larger canvas: a rank that went ahead with its local canvas size while the
+  // GOF-wide maximum was still being reduced (bench.py, sharded frames) repeats a16..a26 when another rank needed more rows. All
+  // inputs of the canvas stages (packed patch records, depth arenas, source cloud + tree) are still resident.
+  if ( g->stage == 4 && stopAfter == 0 && width >= g->W && height >= g->H && ( width != g->W || height != g->H ) && width % 64 == 0 && height % 64 == 0 ) {
+    for ( auto* fs : g->frames ) fs->decodedSet = false;
+    g->stage = 1;
+  }
   if ( g->stage != 1 && g->stage != 2 ) return PCCB200_ERR_STATE;
   if ( width < g->W || height < g->H || width % 64 || height % 64 ) return PCCB200_ERR_BAD_ARG;
   if ( g->stage == 2 && ( width != g->W || height != g->H || stopAfter == 2 ) ) return PCCB200_ERR_BAD_ARG;
@@ -499,9 +509,18 @@ int pccb200_gof_set_decoded( pccb200_gof* g, int f, const uint8_t* occVideo, con
 int pccb200_generate_point_cloud( pccb200_ctx* ctx, const pccb200_patch* patches, int numPatches, const uint8_t* occVideo, const uint16_t* geo0,
                                   const uint16_t* geo1, size_t width, size_t height, int occupancyPrecision, size_t capacity, int16_t* xyz,
                                   uint32_t* pointToPixel, uint32_t* partition, uint16_t* boundary, size_t* recPoints ) {
-  if ( !ctx || numPatches < 0 || ( numPatches && !patches ) || !occVideo || !geo0 || !geo1 || !recPoints || width % 16 || height % 16 ||
-       occupancyPrecision < 1 || 16 % occupancyPrecision )
+  if ( !ctx || numPatches < 0 || ( numPatches && !patches ) || !occVideo || !geo0 || !geo1 || !recPoints || width == 0 || height == 0 ||
+       width % 16 || height % 16 || width > 65536 || height > 65536 || occupancyPrecision < 1 || 16 % occupancyPrecision )
     return PCCB200_ERR_BAD_ARG;
+  // The patch records come from a bitstream (PCCDecoder.cpp:900-1040): nothing in them is trusted. Every patch must lie inside
+  // the canvas in 16-pixel blocks, in its orientation (PCCPatch::patchBlock2CanvasBlock, PCCPatch.cpp:253-308).
+  for ( int i = 0; i < numPatches; ++i ) {
+    const pccb200_patch& m = patches[i];
+    if ( m.view_id < 0 || m.view_id > 5 || ( m.orientation != 0 && m.orientation != 1 ) ) return PCCB200_ERR_UNSUPPORTED;
+    const long long bw = (long long)( width / 16 ), bh = (long long)( height / 16 );
+    const long long su = m.orientation == 0 ? m.size_u0 : m.size_v0, sv = m.orientation == 0 ? m.size_v0 : m.size_u0;
+    if ( m.u0 < 0 || m.v0 < 0 || m.size_u0 <= 0 || m.size_v0 <= 0 || m.u0 + su > bw || m.v0 + sv > bh ) return PCCB200_ERR_BAD_ARG;
+  }
   return guarded( ctx, [&]() -> int {
     if ( ctx->framePool.empty() ) {
       ctx->framePool.emplace_back( new FrameState() );
@@ -517,7 +536,6 @@ int pccb200_generate_point_cloud( pccb200_ctx* ctx, const pccb200_patch* patches
     int                      maxBlocks = 1;
     for ( int i = 0; i < P; ++i ) {
       const pccb200_patch& m = patches[i];
-      if ( m.view_id < 0 || m.view_id > 5 || ( m.orientation != 0 && m.orientation != 1 ) ) return PCCB200_ERR_UNSUPPORTED;
       CanvasPatch& c = cp[i];
       c.viewId = m.view_id, c.u1 = m.u1, c.v1 = m.v1, c.d1 = m.d1, c.sizeU = m.size_u, c.sizeV = m.size_v, c.sizeU0 = m.size_u0, c.sizeV0 = m.size_v0;
       c.u0 = m.u0, c.v0 = m.v0, c.orientation = m.orientation, c.pad = 0, c.depthOff = c.occOff = 0;

@@ -490,6 +490,8 @@ void kdBuild( KdTree& t, const short4* xyz4, size_t n, cudaStream_t s ) {
 void kdKnn( const KdTree& t, const short4* queries, size_t nq, const uint32_t* queryOrder, int k, uint32_t* outIdx,
             float* outDist, cudaStream_t s ) {
   if ( nq == 0 ) return;
+  // the traversal stack holds one far child per level: a deeper tree (degenerate input) would overflow it silently
+  if ( t.numLevels + 2 > kMaxStack ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   Box6 rb;
   for ( int d = 0; d < 6; ++d ) rb.v[d] = t.rootBox[d];
   const int TB = 128, grid = divUp( nq, TB );

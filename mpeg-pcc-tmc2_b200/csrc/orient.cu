@@ -553,11 +553,16 @@ void orientWalkBatch( OrientScratch* const* frames, int count, DevBuf<unsigned c
       smem = std::max( smem, frames[i]->walkSmem );
     }
   if ( args.empty() ) return;
-  {  // the limit is a per-function global: raise it once to the maximum any frame may need
-    static std::once_flag once;
-    cudaError_t           err = cudaSuccess;
-    std::call_once( once, [&]() { err = cudaFuncSetAttribute( kWalk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 ); } );
-    PCC_CUDA( err );
+  {  // the limit is per function AND per device: raise it once per device to the maximum any frame may need
+    static std::mutex m;
+    static bool       raised[64] = { false };
+    int               dev        = 0;
+    PCC_CUDA( cudaGetDevice( &dev ) );
+    std::lock_guard<std::mutex> lk( m );
+    if ( dev < 0 || dev >= 64 || !raised[dev] ) {
+      PCC_CUDA( cudaFuncSetAttribute( kWalk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 ) );
+      if ( dev >= 0 && dev < 64 ) raised[dev] = true;
+    }
   }
   // device block: the frames' arguments, then one (start, end) %globaltimer pair per frame
   const size_t argBytes = ( args.size() * sizeof( WalkArgs ) + 15 ) & ~size_t( 15 );

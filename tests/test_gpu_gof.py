@@ -109,3 +109,50 @@ def test_encode_gof_parameter_variations(name, prec, overrides, oracle, product)
     for k, v in overrides.items():
         setattr(prm, k, v)
     assert compare_gof(product.encode_gof(frames, prm, occupancy_precision=prec), oracle.encode_gof(frames, prm, occupancy_precision=prec)) == []
+
+
+def test_reform_on_larger_canvas(oracle, product):
+    """bench.py's sharded protocol: a rank forms the images on its local canvas size and, if the GOF-wide maximum turns out larger,
+    again on that one (pccb200_gof_resume on a finished GOF) - the second result must equal a one-shot run on the larger canvas"""
+    frames = [synth.figure(scale=0.2, seed=5, frame=0), synth.double_sheet(n_side=40, seed=3)]
+    prm = ctc_seg_params(bits=10, iterations=6, weight=product.weight_normal(frames[0][0], 11))
+    g = bindings.ProductGof(product, frames, prm, 4)
+    W, H, _ = g.dims(0)
+    g.resume(W, H, 0)
+    small = [g.fetch(f, bindings.GOF_GEO0) for f in range(2)]
+    g.resume(W, H + 128, 0)
+    assert g.dims(0)[:2] == (W, H + 128)
+    want = oracle.encode_gof(frames, prm, canvas=(W, H + 128))
+    for f in range(2):
+        for what in bindings.GOF_NAMES:
+            assert np.array_equal(g.fetch(f, what), want[f].data[what]), "frame %d %s after re-forming" % (f, bindings.GOF_NAMES[what])
+        assert small[f].size < want[f].data[bindings.GOF_GEO0].size
+    g.free()
+
+
+def test_unsupported_parameters_are_rejected(product):
+    """anything outside the implemented path is PCCB200_ERR_UNSUPPORTED, never a silently different result"""
+    frames = [synth.sphere(radius=12, center=40)]
+    for field, value in (("voxel_dim_refine", 2), ("voxel_dim_refine", 1), ("voxel_dim_refine", 8), ("search_radius_refine", 4096),
+                         ("nn_normal_estimation", 8), ("map_count_minus1", 0)):
+        prm = ctc_seg_params(bits=10, iterations=2, weight=(1.0, 1.0, 1.0))
+        setattr(prm, field, value)
+        with pytest.raises(RuntimeError, match="error -6"):
+            product.encode_gof(frames, prm)
+
+
+def test_decoder_rejects_patches_outside_the_canvas(oracle, product):
+    """the decoder-side entry point is fed from a bitstream: negative or oversized placements must be refused, not rasterised"""
+    frames = [synth.sphere(radius=16, center=50, seed=1)]
+    prm = ctc_seg_params(bits=10, iterations=3, weight=product.weight_normal(frames[0][0], 11))
+    fr = oracle.encode_gof(frames, prm, stop_after=3)[0]
+    args = (fr[bindings.GOF_OM_VIDEO], fr[bindings.GOF_GEO0], fr[bindings.GOF_GEO1], fr.width, fr.height)
+    good = product.generate_point_cloud(fr.patches.patches, *args)
+    assert np.array_equal(good["xyz"].ravel(), fr[bindings.GOF_REC_XYZ])
+    for field, value in (("u0", -1), ("v0", -3), ("size_u0", 0), ("size_v0", -2), ("u0", fr.width // 16), ("v0", fr.height // 16)):
+        bad = fr.patches.patches.copy()
+        bad[field][0] = value
+        with pytest.raises(RuntimeError):
+            product.generate_point_cloud(bad, *args)
+    with pytest.raises(RuntimeError):
+        product.generate_point_cloud(fr.patches.patches, fr[bindings.GOF_OM_VIDEO], fr[bindings.GOF_GEO0], fr[bindings.GOF_GEO1], 0, fr.height)

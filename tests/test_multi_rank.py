@@ -62,3 +62,67 @@ def test_sharded_gof_equals_unsharded(tmp_path, oracle):
         for k, v in fr.data.items():
             assert np.array_equal(got[str(k)], v), "frame %d product %s differs between sharded and unsharded runs" % (f, bindings.GOF_NAMES[k])
     assert len(local_heights) > 1 or whole[0].height == 1280, "test should exercise a shard whose local canvas is smaller"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the protocol bench.py runs (mpeg-pcc-tmc2_b200/sharding.py): batched all-reduce from a comm thread, image formation on the LOCAL
+# canvas size first, re-formed on the reduced size when another rank needed more rows
+def _exchange_worker(rank, world, port, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "mpeg-pcc-tmc2_b200"))
+    import bindings
+    from sharding import CanvasExchange
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    group = dist.new_group(backend="gloo")
+    orc = bindings.Oracle()
+    frames = _frames()
+    w = torch.tensor(orc.weight_normal(frames[0][0], 11)) if rank == 0 else torch.zeros(3, dtype=torch.float64)
+    dist.broadcast(w, 0)
+    prm = bindings.ctc_seg_params(bits=10, iterations=6, weight=tuple(float(x) for x in w))
+    # five GOFs: in GOF 0 and 3 the ranks hold different frames (rank 1's need the taller canvas), in the others the same ones
+    gofs = [frames[rank::world], frames[:2], frames[:2], frames[rank::world], frames[1:2]]
+    ex = CanvasExchange(dist, len(gofs), batch=2, group=group, device=None)
+    reformed = []
+    import threading
+
+    def lane(which):   # two lanes per rank, GOFs taken alternately in increasing order (as bench.py does: a lane never waits for a GOF it will post later)
+        for g in which:
+            packed = orc.encode_gof(gofs[g], prm, stop_after=1)
+            W, H = packed[0].width, packed[0].height
+            ex.post(g, W, H)
+            full = orc.encode_gof(gofs[g], prm, canvas=(W, H))            # ahead on the local size
+            Wg, Hg = ex.wait(g)
+            if (Wg, Hg) != (W, H):
+                reformed.append(g)
+                full = orc.encode_gof(gofs[g], prm, canvas=(Wg, Hg))
+            np.savez(os.path.join(out_dir, "x_rank%d_gof%d.npz" % (rank, g)), canvas=np.array([Wg, Hg]),
+                     **{"f%d_%d" % (i, k): v for i, fr in enumerate(full) for k, v in fr.data.items()})
+    ths = [threading.Thread(target=lane, args=([0, 2, 4],)), threading.Thread(target=lane, args=([1, 3],))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    ex.close()
+    np.save(os.path.join(out_dir, "x_stats_%d.npy" % rank), np.array([ex.collectives, len(reformed)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_canvas_exchange_protocol(tmp_path, oracle):
+    import bindings
+    world, port = 2, 29331 + (os.getpid() % 200)
+    mp.spawn(_exchange_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    frames = _frames()
+    prm = bindings.ctc_seg_params(bits=10, iterations=6, weight=oracle.weight_normal(frames[0][0], 11))
+    whole = oracle.encode_gof(frames, prm)                       # GOF 0 / 3 unsharded: frames 0..3
+    stats = [np.load(tmp_path / ("x_stats_%d.npy" % r)) for r in range(world)]
+    assert stats[0][0] == stats[1][0] and 3 <= int(stats[0][0]) <= 5, "5 GOFs in windows of up to 2: 3..5 collectives, the same on every rank"
+    assert sum(int(s[1]) for s in stats) >= 1 or whole[0].height == 1280, "a rank with the smaller local canvas must re-form"
+    for g in (0, 3):
+        for rank in range(world):
+            got = np.load(tmp_path / ("x_rank%d_gof%d.npz" % (rank, g)))
+            assert tuple(got["canvas"]) == (whole[0].width, whole[0].height)
+            for i, f in enumerate(range(rank, len(frames), world)):
+                for k, v in whole[f].data.items():
+                    assert np.array_equal(got["f%d_%d" % (i, k)], v), "GOF %d frame %d product %s" % (g, f, bindings.GOF_NAMES[k])
