@@ -215,6 +215,28 @@ enum {
 };
 size_t pccb200_gof_get( pccb200_gof* gof, int f, int what, void* dst );
 
+/* ---- post-reconstruction chain: what follows generatePointCloud in PCCEncoder::encode
+ * (PccLibEncoder/source/PCCEncoder.cpp:556-719) and PCCDecoder::decode (PccLibDecoder/source/PCCDecoder.cpp:356-475) under the CTC.
+ * Host buffers in / out like every other entry point. */
+
+/* PCCCodec::smoothPointCloudPostprocess, grid-based geometry smoothing (PccLibCommon/source/PCCCodec.cpp:54-150, 982-1168;
+ * CTC: gridSmoothing on, gridSize 8, thresholdSmoothing 64). In place: xyz (n x 3) receives the smoothed positions, boundary[]
+ * the updated boundary point types (a moved point becomes type 3, PCCCodec.cpp:1139); partition[] = patch index of every point. */
+int pccb200_smooth_geometry( pccb200_ctx* ctx, int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int grid_size,
+                             double threshold );
+
+/* PCCPointSet3::transferColors16bitBP as encode / decode call it after the smoothing (PccLibCommon/source/PCCPointSet.cpp:1126-1485:
+ * 8-NN forward, 1-NN backward votes with the colour gate, fp64 sums in std::sort order): new 16-bit colours, in place in tgt_col
+ * (T x 3), for the target points of boundary type 3; src = the cloud before smoothing with its colours. */
+int pccb200_transfer_colors16_smoothed( pccb200_ctx* ctx, const int16_t* src_xyz, const uint16_t* src_col, size_t S, const int16_t* tgt_xyz,
+                                        uint16_t* tgt_col, const uint16_t* tgt_boundary, size_t T );
+
+/* The two ends of colorPointCloud (PCCCodec.cpp:1319-1460): the decoded attribute frame YUV 4:2:0 (8 bit, planes Y, U, V) ->
+ * YUV 4:4:4 16 bit (PCCInternalColorConverter "YUV420ToYUV444_16_...": PccLibColorConverter/source/PCCInternalColorConverter.cpp:
+ * 425-470, up-sampling filter 0), planar 3 x W x H; and PCCPointSet3::convertYUV16ToRGB8 of the point colours (n x 3 -> n x 3). */
+int pccb200_yuv420_to_yuv444_16( pccb200_ctx* ctx, const uint8_t* yuv420, size_t width, size_t height, uint16_t* yuv444 );
+int pccb200_yuv16_to_rgb8( pccb200_ctx* ctx, const uint16_t* yuv, size_t n, uint8_t* rgb );
+
 #ifdef __cplusplus
 }
 #endif

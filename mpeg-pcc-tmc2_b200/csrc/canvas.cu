@@ -14,6 +14,8 @@
 
 #include <algorithm>
 
+#include <mutex>
+
 #include "stages.cuh"
 
 namespace pccb200 {
@@ -396,17 +398,25 @@ __device__ __forceinline__ int mean4w( int p1, int w1, int p2, int w2, int p3, i
   return ( p1 * w1 + p2 * w2 + p3 * w3 + p4 * w4 ) / ( w1 + w2 + w3 + w4 );
 }
 
+// Both attribute frames (T0, T1) go through the pyramid in the SAME launches (blockIdx.y selects the frame; the occupancy pyramid
+// is common to both), and the small levels (at most kTailMaxPixels pixels) are done by ONE CTA per frame in shared memory
+// (kPushPullTail): pulls down to the coarsest level, pushes and all smoothing passes back up.
+struct Pair {
+  ushort4* p[2];
+};
+struct ConstPair {
+  const ushort4* p[2];
+};
+
 // pull: occupancy-weighted 2x2 mean (values truncated to 8 bits as the reference's unsigned char locals do)
-__global__ void kPull( const ushort4* __restrict__ img, const uint8_t* __restrict__ occ, int W, int H, ushort4* __restrict__ mip,
-                       uint8_t* __restrict__ mipOcc, int nw, int nh ) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= nw * nh ) return;
-  const int  x = i % nw, y = i / nw, X = x << 1, Y = y << 1;
+__device__ __forceinline__ void pullPixel( const ushort4* __restrict__ img, const uint8_t* __restrict__ occ, int W, int H, int x, int y, ushort4& out,
+                                           uint8_t& o ) {
+  const int  X = x << 1, Y = y << 1;
   const bool in2 = X + 1 < W, in3 = Y + 1 < H;
   const int  w1 = occ[size_t( Y ) * W + X] ? 255 : 0, w2 = ( in2 && occ[size_t( Y ) * W + X + 1] ) ? 255 : 0,
             w3 = ( in3 && occ[size_t( Y + 1 ) * W + X] ) ? 255 : 0, w4 = ( in2 && in3 && occ[size_t( Y + 1 ) * W + X + 1] ) ? 255 : 0;
-  ushort4 out = make_ushort4( 0, 0, 0, 0 );
-  uint8_t o   = 0;
+  out = make_ushort4( 0, 0, 0, 0 );
+  o   = 0;
   if ( w1 + w2 + w3 + w4 > 0 ) {
     const ushort4 z  = make_ushort4( 0, 0, 0, 0 );
     const ushort4 a  = img[size_t( Y ) * W + X], b = in2 ? img[size_t( Y ) * W + X + 1] : z, c = in3 ? img[size_t( Y + 1 ) * W + X] : z,
@@ -416,39 +426,116 @@ __global__ void kPull( const ushort4* __restrict__ img, const uint8_t* __restric
     out.z            = mean4w( a.z & 0xff, w1, b.z & 0xff, w2, c.z & 0xff, w3, d.z & 0xff, w4 );
     o                = 1;
   }
-  mip[i]    = out;
-  mipOcc[i] = o;
+}
+__global__ void kPull( ConstPair img, const uint8_t* __restrict__ occ, int W, int H, Pair mip, uint8_t* __restrict__ mipOcc, int nw, int nh ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= nw * nh ) return;
+  ushort4 out;
+  uint8_t o;
+  pullPixel( img.p[blockIdx.y], occ, W, H, i % nw, i / nw, out, o );
+  mip.p[blockIdx.y][i] = out;
+  if ( blockIdx.y == 0 ) mipOcc[i] = o;
 }
 
 // push: unoccupied pixels take the bilinear-like blend (144,48,48,16) of the coarser level
-__global__ void kPushFill( ushort4* __restrict__ img, const uint8_t* __restrict__ occ, int W, int H, const ushort4* __restrict__ mip, int w, int h ) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= W * H || occ[i] ) return;
-  const int  X = i % W, Y = i / W, x = X >> 1, y = Y >> 1;
+__device__ __forceinline__ ushort4 pushPixel( const ushort4* __restrict__ mip, int w, int h, int X, int Y, unsigned short keepW ) {
+  const int  x = X >> 1, y = Y >> 1;
   const int  dx = ( X & 1 ) ? 1 : -1, dy = ( Y & 1 ) ? 1 : -1;
   const bool okx = dx < 0 ? x > 0 : x < w - 1, oky = dy < 0 ? y > 0 : y < h - 1;
   const ushort4 z = make_ushort4( 0, 0, 0, 0 );
   const ushort4 v = mip[size_t( y ) * w + x], vx = okx ? mip[size_t( y ) * w + x + dx] : z, vy = oky ? mip[size_t( y + dy ) * w + x] : z,
                 vd = ( okx && oky ) ? mip[size_t( y + dy ) * w + x + dx] : z;
   const int wx = okx ? 48 : 0, wy = oky ? 48 : 0, wd = ( okx && oky ) ? 16 : 0;
-  img[i] = make_ushort4( mean4w( v.x, 144, vx.x, wx, vy.x, wy, vd.x, wd ), mean4w( v.y, 144, vx.y, wx, vy.y, wy, vd.y, wd ),
-                         mean4w( v.z, 144, vx.z, wx, vy.z, wy, vd.z, wd ), img[i].w );
+  return make_ushort4( mean4w( v.x, 144, vx.x, wx, vy.x, wy, vd.x, wd ), mean4w( v.y, 144, vx.y, wx, vy.y, wy, vd.y, wd ),
+                       mean4w( v.z, 144, vx.z, wx, vy.z, wy, vd.z, wd ), keepW );
+}
+__global__ void kPushFill( Pair img, const uint8_t* __restrict__ occ, int W, int H, ConstPair mip, int w, int h ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= W * H || occ[i] ) return;
+  ushort4* im = img.p[blockIdx.y];
+  im[i]       = pushPixel( mip.p[blockIdx.y], w, h, i % W, i / W, im[i].w );
 }
 
 // one Jacobi pass of the 8-neighbour smoothing of unoccupied pixels (occupied ones are copied through)
-__global__ void kSmooth8( const ushort4* __restrict__ src, ushort4* __restrict__ dst, const uint8_t* __restrict__ occ, int W, int H ) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= W * H ) return;
-  if ( occ[i] ) {
-    dst[i] = src[i];
-    return;
-  }
+__device__ __forceinline__ ushort4 smoothPixel( const ushort4* __restrict__ src, const uint8_t* __restrict__ occ, int W, int H, int i ) {
+  if ( occ[i] ) return src[i];
   const int x = i % W, y = i / W;
   const int x1 = x > 0 ? x - 1 : x, y1 = y > 0 ? y - 1 : y, x2 = x < W - 1 ? x + 1 : x, y2 = y < H - 1 ? y + 1 : y;
   auto      at = [&]( int xx, int yy ) { return src[size_t( yy ) * W + xx]; };
   const ushort4 a = at( x1, y1 ), b = at( x2, y1 ), c = at( x1, y2 ), d = at( x2, y2 ), e = at( x1, y ), f = at( x2, y ), g = at( x, y1 ), h = at( x, y2 );
-  dst[i] = make_ushort4( ( a.x + b.x + c.x + d.x + e.x + f.x + g.x + h.x + 4 ) >> 3, ( a.y + b.y + c.y + d.y + e.y + f.y + g.y + h.y + 4 ) >> 3,
-                         ( a.z + b.z + c.z + d.z + e.z + f.z + g.z + h.z + 4 ) >> 3, src[i].w );
+  return make_ushort4( ( a.x + b.x + c.x + d.x + e.x + f.x + g.x + h.x + 4 ) >> 3, ( a.y + b.y + c.y + d.y + e.y + f.y + g.y + h.y + 4 ) >> 3,
+                       ( a.z + b.z + c.z + d.z + e.z + f.z + g.z + h.z + 4 ) >> 3, src[i].w );
+}
+__global__ void kSmooth8( ConstPair src, Pair dst, const uint8_t* __restrict__ occ, int W, int H ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ( i >= W * H ) return;
+  dst.p[blockIdx.y][i] = smoothPixel( src.p[blockIdx.y], occ, W, H, i );
+}
+
+// group dilation of the two attribute maps (PCCEncoder.cpp:391-413): unoccupied pixels take the rounded mean of T0 and T1
+__global__ void kAttrGroupDilate( ushort4* __restrict__ t0, ushort4* __restrict__ t1, const uint8_t* __restrict__ occ, size_t n ) {
+  const size_t q = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( q >= n || occ[q] ) return;
+  const ushort4 a = t0[q], b = t1[q];
+  const ushort4 m = make_ushort4( ( ( a.x & 0xff ) + ( b.x & 0xff ) + 1 ) >> 1, ( ( a.y & 0xff ) + ( b.y & 0xff ) + 1 ) >> 1,
+                                  ( ( a.z & 0xff ) + ( b.z & 0xff ) + 1 ) >> 1, 0 );
+  t0[q] = make_ushort4( m.x, m.y, m.z, a.w ), t1[q] = make_ushort4( m.x, m.y, m.z, b.w );
+}
+
+// the small levels of the pyramid in one CTA per frame: level 0 of `a` is the finest level handled here (in global memory:
+// base / baseOcc), the coarser ones live in shared memory only
+constexpr int kTailMaxPixels = 6400;  // 80 x 80
+constexpr int kTailLevels    = 12;
+constexpr int kTailThreads   = 512;
+struct TailArgs {
+  int n;  // levels incl. the base level
+  int w[kTailLevels], h[kTailLevels];
+  int firstIters;  // smoothing passes after the coarsest push (grows by one per level, at most 16)
+};
+__global__ void __launch_bounds__( kTailThreads ) kPushPullTail( Pair base, const uint8_t* __restrict__ baseOcc, TailArgs a ) {
+  extern __shared__ __align__( 16 ) unsigned char tailSmem[];
+  ushort4* img[kTailLevels];
+  uint8_t* occ[kTailLevels];
+  size_t   px = 0;
+  for ( int l = 0; l < a.n; ++l ) px += size_t( a.w[l] ) * a.h[l];
+  {
+    ushort4* ip = reinterpret_cast<ushort4*>( tailSmem );
+    uint8_t* op = reinterpret_cast<uint8_t*>( ip + px + size_t( a.w[0] ) * a.h[0] );  // after the images and the ping-pong buffer
+    for ( int l = 0; l < kTailLevels; ++l ) {
+      img[l] = ip, occ[l] = op;
+      if ( l < a.n ) ip += size_t( a.w[l] ) * a.h[l], op += size_t( a.w[l] ) * a.h[l];
+    }
+  }
+  ushort4* const tmp = reinterpret_cast<ushort4*>( tailSmem ) + px;
+  ushort4* const g   = base.p[blockIdx.x];
+  const int      n0  = a.w[0] * a.h[0];
+  for ( int i = threadIdx.x; i < n0; i += kTailThreads ) img[0][i] = g[i], occ[0][i] = baseOcc[i];
+  __syncthreads();
+  for ( int l = 1; l < a.n; ++l ) {
+    const int nw = a.w[l], nh = a.h[l];
+    for ( int i = threadIdx.x; i < nw * nh; i += kTailThreads ) pullPixel( img[l - 1], occ[l - 1], a.w[l - 1], a.h[l - 1], i % nw, i / nw, img[l][i], occ[l][i] );
+    __syncthreads();
+  }
+  int iters = a.firstIters;
+  for ( int l = a.n - 1; l >= 1; --l ) {
+    const int dw = a.w[l - 1], dh = a.h[l - 1], n = dw * dh;
+    for ( int i = threadIdx.x; i < n; i += kTailThreads )
+      if ( !occ[l - 1][i] ) img[l - 1][i] = pushPixel( img[l], a.w[l], a.h[l], i % dw, i / dw, img[l - 1][i].w );
+    __syncthreads();
+    ushort4 *src = img[l - 1], *dst = tmp;
+    for ( int it = 0; it < iters; ++it ) {
+      for ( int i = threadIdx.x; i < n; i += kTailThreads ) dst[i] = smoothPixel( src, occ[l - 1], dw, dh, i );
+      __syncthreads();
+      ushort4* t = src;
+      src = dst, dst = t;
+    }
+    if ( src != img[l - 1] ) {
+      for ( int i = threadIdx.x; i < n; i += kTailThreads ) img[l - 1][i] = src[i];
+      __syncthreads();
+    }
+    iters = min( iters + 1, 16 );
+  }
+  for ( int i = threadIdx.x; i < n0; i += kTailThreads ) g[i] = img[0][i];
 }
 
 }  // namespace
@@ -542,7 +629,7 @@ void formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, si
   }
   kUpsampleOccupancy<<<divUp( Q, 256 ), 256, 0, s>>>( om, W, H, prec, at.occ );
   for ( int m = 0; m < 2; ++m ) kToPlanes<<<divUp( Q, 256 ), 256, 0, s>>>( at.T[m], Q, out.rawPlanes[m] );
-  // push-pull pyramid (shared by both maps: levels are rebuilt per map)
+  // push-pull pyramid, both frames per launch; the small levels in one CTA per frame (kPushPullTail)
   std::vector<int> lw, lh;
   {
     int w = W, h = H;
@@ -553,32 +640,64 @@ void formAttributeImages( const uint32_t* pointToPixel, const uchar4* recRgb, si
     }
   }
   const int L = int( lw.size() );
-  if ( int( at.mip.size() ) < L ) at.mip.resize( L ), at.mipOcc.resize( L );
-  for ( int l = 0; l < L; ++l ) at.mip[l].reserve( size_t( lw[l] ) * lh[l] ), at.mipOcc[l].reserve( size_t( lw[l] ) * lh[l] );
-  for ( int m = 0; m < 2; ++m ) {
-    for ( int l = 0; l < L; ++l ) {
-      const ushort4* src  = l == 0 ? at.T[m].p : at.mip[l - 1].p;
-      const uint8_t* socc = l == 0 ? at.occ.p : at.mipOcc[l - 1].p;
-      const int      sw = l == 0 ? W : lw[l - 1], sh = l == 0 ? H : lh[l - 1];
-      kPull<<<divUp( size_t( lw[l] ) * lh[l], 256 ), 256, 0, s>>>( src, socc, sw, sh, at.mip[l], at.mipOcc[l], lw[l], lh[l] );
-    }
-    int iters = 4;
-    for ( int l = L - 1; l >= 0; --l ) {
-      ushort4*       dst  = l == 0 ? at.T[m].p : at.mip[l - 1].p;
-      const uint8_t* docc = l == 0 ? at.occ.p : at.mipOcc[l - 1].p;
-      const int      dw = l == 0 ? W : lw[l - 1], dh = l == 0 ? H : lh[l - 1];
-      const size_t   n  = size_t( dw ) * dh;
-      kPushFill<<<divUp( n, 256 ), 256, 0, s>>>( dst, docc, dw, dh, at.mip[l], lw[l], lh[l] );
-      ushort4 *a = dst, *b = at.tmp.p;
-      for ( int it = 0; it < iters; ++it ) {
-        kSmooth8<<<divUp( n, 256 ), 256, 0, s>>>( a, b, docc, dw, dh );
-        std::swap( a, b );
-      }
-      if ( a != dst ) PCC_CUDA( cudaMemcpyAsync( dst, a, n * sizeof( ushort4 ), cudaMemcpyDeviceToDevice, s ) );
-      iters = std::min( iters + 1, 16 );
-    }
-    kToPlanes<<<divUp( Q, 256 ), 256, 0, s>>>( at.T[m], Q, out.planes[m] );
+  int       T = 0;  // first level small enough for the tail kernel (its finest level, kept in global memory)
+  while ( T < L - 1 && size_t( lw[T] ) * lh[T] > size_t( kTailMaxPixels ) ) ++T;
+  const bool useTail = T < L - 1 && size_t( lw[T] ) * lh[T] <= size_t( kTailMaxPixels ) && L - T <= kTailLevels;
+  if ( !useTail ) T = L - 1;  // (every level goes through the per-level launches)
+  if ( int( at.mip.size() ) < 2 * L ) at.mip.resize( 2 * L );
+  if ( int( at.mipOcc.size() ) < L ) at.mipOcc.resize( L );
+  at.tmp2.reserve( Q );
+  for ( int l = 0; l <= T; ++l ) {
+    at.mip[l].reserve( size_t( lw[l] ) * lh[l] ), at.mip[L + l].reserve( size_t( lw[l] ) * lh[l] );
+    at.mipOcc[l].reserve( size_t( lw[l] ) * lh[l] );
   }
+  auto level = [&]( int l ) { return l < 0 ? Pair{ { at.T[0].p, at.T[1].p } } : Pair{ { at.mip[l].p, at.mip[L + l].p } }; };
+  auto constant = []( Pair p ) { return ConstPair{ { p.p[0], p.p[1] } }; };
+  for ( int l = 0; l <= T; ++l ) {  // pulls down to the tail's base level
+    const uint8_t* socc = l == 0 ? at.occ.p : at.mipOcc[l - 1].p;
+    const int      sw = l == 0 ? W : lw[l - 1], sh = l == 0 ? H : lh[l - 1];
+    kPull<<<dim3( divUp( size_t( lw[l] ) * lh[l], 256 ), 2 ), 256, 0, s>>>( constant( level( l - 1 ) ), socc, sw, sh, level( l ), at.mipOcc[l], lw[l], lh[l] );
+  }
+  int iters = 4;
+  if ( useTail ) {
+    TailArgs a;
+    a.n = L - T;
+    size_t px = 0;
+    for ( int l = 0; l < kTailLevels; ++l ) a.w[l] = a.h[l] = 0;
+    for ( int l = T; l < L; ++l ) a.w[l - T] = lw[l], a.h[l - T] = lh[l], px += size_t( lw[l] ) * lh[l];
+    a.firstIters      = 4;
+    const size_t smem = ( px + size_t( lw[T] ) * lh[T] ) * sizeof( ushort4 ) + px + 16;
+    {
+      static std::mutex           m;
+      static bool                 raised[64] = { false };
+      int                         dev        = 0;
+      PCC_CUDA( cudaGetDevice( &dev ) );
+      std::lock_guard<std::mutex> lk( m );
+      if ( dev < 0 || dev >= 64 || !raised[dev] ) {
+        PCC_CUDA( cudaFuncSetAttribute( kPushPullTail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 ) );
+        if ( dev >= 0 && dev < 64 ) raised[dev] = true;
+      }
+    }
+    kPushPullTail<<<2, kTailThreads, smem, s>>>( level( T ), at.mipOcc[T], a );
+    iters = std::min( 4 + ( L - 1 - T ), 16 );
+  }
+  for ( int l = T; l >= 0; --l ) {  // pushes of the large levels: destination = level l-1 (the frames themselves for l = 0)
+    const uint8_t* docc = l == 0 ? at.occ.p : at.mipOcc[l - 1].p;
+    const int      dw = l == 0 ? W : lw[l - 1], dh = l == 0 ? H : lh[l - 1];
+    const size_t   n  = size_t( dw ) * dh;
+    const Pair     dst = level( l - 1 );
+    kPushFill<<<dim3( divUp( n, 256 ), 2 ), 256, 0, s>>>( dst, docc, dw, dh, constant( level( l ) ), lw[l], lh[l] );
+    Pair a = dst, b = Pair{ { at.tmp.p, at.tmp2.p } };
+    for ( int it = 0; it < iters; ++it ) {
+      kSmooth8<<<dim3( divUp( n, 256 ), 2 ), 256, 0, s>>>( constant( a ), b, docc, dw, dh );
+      std::swap( a, b );
+    }
+    if ( a.p[0] != dst.p[0] )
+      for ( int m = 0; m < 2; ++m ) PCC_CUDA( cudaMemcpyAsync( dst.p[m], a.p[m], n * sizeof( ushort4 ), cudaMemcpyDeviceToDevice, s ) );
+    iters = std::min( iters + 1, 16 );
+  }
+  kAttrGroupDilate<<<divUp( Q, 256 ), 256, 0, s>>>( at.T[0], at.T[1], at.occ, Q );
+  for ( int m = 0; m < 2; ++m ) kToPlanes<<<divUp( Q, 256 ), 256, 0, s>>>( at.T[m], Q, out.planes[m] );
   PCC_LAUNCH_CHECK();
 }
 

@@ -22,16 +22,17 @@ struct KdTree {
   DevBuf<int4>      nodes;  // node 0 is the root
   int               rootBox[6] = {0, 0, 0, 0, 0, 0};  // tight lo[3], hi[3]
   int               numNodes   = 0;
-  int               numLevels  = 0;
+  int               numLevels  = 0;  // depth of the tree (bounds the search stack)
+  int               lastTopLevels = 0;  // level-synchronous levels the previous build needed (kdtree.cu)
   // build scratch (kept for reuse)
-  DevBuf<uint32_t>  tmpA, tmpB, flags, scanOut, scanTmp;
-  DevBuf<int>       slotOf, slotOfNext;
+  DevBuf<uint32_t>  tmpA, tmpB, flags, scanOut, scanTmp;  // flags / scanOut: the scans of the two sweeps; scanTmp: look-back control blocks
+  DevBuf<int>       slotOf, slotOfNext;                    // slotOfNext: records of the local subtrees
   DevBuf<int>       slotI[2];  // per-slot int records, double buffered (see kdtree.cu)
   DevBuf<int>       counters;
-  PinBuf<int>       hostInts;  // page-locked landing zone of the per-level read-back (a pageable copy would spin in the driver)
+  PinBuf<int>       hostInts;  // page-locked landing zone of the one read-back per tree (a pageable copy would spin in the driver)
 };
 
-// xyz4: n points already on the device as short4. Builds nodes/vind/ptsT on stream s (host-synchronising).
+// xyz4: n points already on the device as short4. Builds nodes/vind/ptsT on stream s (one host synchronisation at the end).
 void kdBuild( KdTree& t, const short4* xyz4, size_t n, cudaStream_t s );
 
 // k-NN (k <= 16) of nq queries (short4, device). Outputs row-major nq x k, rows in query order:

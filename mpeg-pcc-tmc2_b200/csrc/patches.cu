@@ -192,35 +192,58 @@ __device__ __forceinline__ void relaxMax( int* addr, int v ) {
   if ( v > __ldcg( addr ) ) atomicMax( addr, v );
 }
 
+// Points of a warp almost always belong to the same patch (the input order is spatially coherent): the warp reduces with
+// redux.sync and one lane issues the atomics; mixed warps fall back to per-lane relaxed atomics.
 __global__ void kMinUV( const short4* __restrict__ pts, const uint8_t* __restrict__ partition, const int* __restrict__ member, int n,
                         PatchStats* stats ) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= n ) return;
-  const int m = member[i];
+  const int      i   = blockIdx.x * blockDim.x + threadIdx.x;
+  const int      m   = i < n ? member[i] : -1;
+  const unsigned act = __ballot_sync( 0xffffffffu, m >= 0 );
   if ( m < 0 ) return;
   const int    view = partition[stats[m].seed];
   const short4 p    = pts[i];
-  relaxMin( &stats[m].minU, axisOf( p, cViewAxes[view][1] ) );
-  relaxMin( &stats[m].minV, axisOf( p, cViewAxes[view][2] ) );
+  const int    u = axisOf( p, cViewAxes[view][1] ), v = axisOf( p, cViewAxes[view][2] );
+  const int    leader = __ffs( act ) - 1;
+  if ( __all_sync( act, m == __shfl_sync( act, m, leader ) ) ) {
+    const int mu = __reduce_min_sync( act, u ), mv = __reduce_min_sync( act, v );
+    if ( ( threadIdx.x & 31 ) == leader ) relaxMin( &stats[m].minU, mu ), relaxMin( &stats[m].minV, mv );
+  } else {
+    relaxMin( &stats[m].minU, u ), relaxMin( &stats[m].minV, v );
+  }
 }
 
 __global__ void kSplitAndBounds( const short4* __restrict__ pts, const uint8_t* __restrict__ partition, int* __restrict__ member, int n,
                                  int maxPatchSize, int splitting, PatchStats* stats ) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i >= n ) return;
-  const int m = member[i];
-  if ( m < 0 ) return;
-  const int    view = partition[stats[m].seed];
-  const short4 p    = pts[i];
-  if ( splitting ) {
-    const int u = axisOf( p, cViewAxes[view][1] ), v = axisOf( p, cViewAxes[view][2] );
-    if ( !( u - stats[m].minU < maxPatchSize && v - stats[m].minV < maxPatchSize ) ) {
-      member[i] = -1;  // consumed by the component, not part of the patch
-      return;
+  int       m = i < n ? member[i] : -1;
+  short4    p = make_short4( 0, 0, 0, 0 );
+  if ( m >= 0 ) {
+    const int view = partition[stats[m].seed];
+    p              = pts[i];
+    if ( splitting ) {
+      const int u = axisOf( p, cViewAxes[view][1] ), v = axisOf( p, cViewAxes[view][2] );
+      if ( !( u - stats[m].minU < maxPatchSize && v - stats[m].minV < maxPatchSize ) ) {
+        member[i] = -1;  // consumed by the component, not part of the patch
+        m         = -1;
+      }
     }
   }
-  relaxMin( &stats[m].bbMin[0], int( p.x ) ), relaxMin( &stats[m].bbMin[1], int( p.y ) ), relaxMin( &stats[m].bbMin[2], int( p.z ) );
-  relaxMax( &stats[m].bbMax[0], int( p.x ) ), relaxMax( &stats[m].bbMax[1], int( p.y ) ), relaxMax( &stats[m].bbMax[2], int( p.z ) );
+  const unsigned act = __ballot_sync( 0xffffffffu, m >= 0 );
+  if ( m < 0 ) return;
+  const int c[3]   = {p.x, p.y, p.z};
+  const int leader = __ffs( act ) - 1;
+  if ( __all_sync( act, m == __shfl_sync( act, m, leader ) ) ) {
+    int lo[3], hi[3];
+#pragma unroll
+    for ( int d = 0; d < 3; ++d ) lo[d] = __reduce_min_sync( act, c[d] ), hi[d] = __reduce_max_sync( act, c[d] );
+    if ( ( threadIdx.x & 31 ) == leader ) {
+#pragma unroll
+      for ( int d = 0; d < 3; ++d ) relaxMin( &stats[m].bbMin[d], lo[d] ), relaxMax( &stats[m].bbMax[d], hi[d] );
+    }
+  } else {
+#pragma unroll
+    for ( int d = 0; d < 3; ++d ) relaxMin( &stats[m].bbMin[d], c[d] ), relaxMax( &stats[m].bbMax[d], c[d] );
+  }
 }
 
 __global__ void kFillU64( unsigned long long* p, size_t n, unsigned long long v ) {

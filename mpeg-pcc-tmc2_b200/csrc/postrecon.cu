@@ -1,7 +1,10 @@
-// postrecon.cu — EXPERIMENTAL (not part of include/pccb200.h yet): kernels of the first post-reconstruction stages (SURVEY.md
-// §8f-1) around the host/device functions of postrecon.cuh. The arithmetic is verified on the CPU against the reference
-// (tests/test_postrecon_functions.py); these kernels have NOT run on a GPU yet (round 1 ended without GPU minutes) - the parked
-// test tests/gpu_pending_postrecon.py is the first thing to run next round. Entry points are prefixed pccb200x_.
+// postrecon.cu — the post-reconstruction chain that follows generatePointCloud in PCCEncoder::encode (PCCEncoder.cpp:556-719) and
+// PCCDecoder::decode (PCCDecoder.cpp:356-475) under the CTC: grid-based geometry smoothing
+// (PCCCodec::smoothPointCloudPostprocess, PCCCodec.cpp:54-150, 982-1168), the YUV420 -> YUV444(16) -> RGB8 conversions around
+// colorPointCloud (PCCCodec.cpp:1319-1460) and the colour transfer onto the smoothed cloud (PCCPointSet3::transferColors16bitBP,
+// PCCPointSet.cpp:1126-1485). Kernels around the host/device functions of postrecon.cuh (whose arithmetic is pinned against the
+// reference on the CPU: tests/test_postrecon_functions.py); GPU parity vs the oracle: tests/test_gpu_postrecon.py.
+// Entry points are declared in include/pccb200.h.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "postrecon.cuh"
@@ -164,7 +167,7 @@ __global__ void kBackwardColours( const uint32_t* __restrict__ moved, size_t M, 
 extern "C" {
 
 // PCCPointSet3::transferColors16bitBP as encode / decode call it: new 16-bit colours (in place) for the target points of boundary type 3
-int pccb200x_transfer_colors16_smoothed( pccb200_ctx* ctx, const int16_t* srcXyz, const uint16_t* srcCol, size_t S, const int16_t* tgtXyz,
+int pccb200_transfer_colors16_smoothed( pccb200_ctx* ctx, const int16_t* srcXyz, const uint16_t* srcCol, size_t S, const int16_t* tgtXyz,
                                          uint16_t* tgtCol, const uint16_t* tgtBoundary, size_t T ) {
   return guarded( ctx, [&]() -> int {
     if ( !srcXyz || !srcCol || !tgtXyz || !tgtCol || !tgtBoundary ) return PCCB200_ERR_BAD_ARG;
@@ -222,7 +225,7 @@ int pccb200x_transfer_colors16_smoothed( pccb200_ctx* ctx, const int16_t* srcXyz
 }
 
 // PCCCodec::smoothPointCloudPostprocess (grid smoothing), in place on host arrays: positions n x 3, boundary point types, patch index
-int pccb200x_smooth_geometry( pccb200_ctx* ctx, int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int gridSize, double threshold ) {
+int pccb200_smooth_geometry( pccb200_ctx* ctx, int16_t* xyz, uint16_t* boundary, const uint32_t* partition, size_t n, int gridSize, double threshold ) {
   return guarded( ctx, [&]() -> int {
     if ( !xyz || !boundary || !partition || gridSize < 2 ) return PCCB200_ERR_BAD_ARG;
     if ( n == 0 ) return PCCB200_OK;
@@ -263,7 +266,7 @@ int pccb200x_smooth_geometry( pccb200_ctx* ctx, int16_t* xyz, uint16_t* boundary
 }
 
 // PCCInternalColorConverter "YUV420ToYUV444_8_0": Y (W*H), U, V ((W/2)*(H/2)) bytes -> three W*H planes of uint16
-int pccb200x_yuv420_to_yuv444_16( pccb200_ctx* ctx, const uint8_t* yuv420, size_t W, size_t H, uint16_t* yuv444 ) {
+int pccb200_yuv420_to_yuv444_16( pccb200_ctx* ctx, const uint8_t* yuv420, size_t W, size_t H, uint16_t* yuv444 ) {
   return guarded( ctx, [&]() -> int {
     if ( !yuv420 || !yuv444 || W % 2 || H % 2 || W == 0 || H == 0 ) return PCCB200_ERR_BAD_ARG;
     cudaStream_t     s = ctx->stream;
@@ -288,7 +291,7 @@ int pccb200x_yuv420_to_yuv444_16( pccb200_ctx* ctx, const uint8_t* yuv420, size_
 }
 
 // PCCPointSet3::convertYUV16ToRGB8 for n points (n x 3 each)
-int pccb200x_yuv16_to_rgb8( pccb200_ctx* ctx, const uint16_t* yuv, size_t n, uint8_t* rgb ) {
+int pccb200_yuv16_to_rgb8( pccb200_ctx* ctx, const uint16_t* yuv, size_t n, uint8_t* rgb ) {
   return guarded( ctx, [&]() -> int {
     if ( !yuv || !rgb ) return PCCB200_ERR_BAD_ARG;
     if ( n == 0 ) return PCCB200_OK;

@@ -232,102 +232,111 @@ struct VoxState {
   uint8_t*  active;
 };
 
-// recount histogram; apply INDIRECT marks; re-derive class/PPI for dirty voxels (updateScores)
-// Also resets the sweep's work list (entries to the "not written yet" sentinel, the three control words to 0).
-__global__ void kRecount( VoxState st, const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
-                          const uint32_t* __restrict__ idsSorted, const uint8_t* __restrict__ partition, int V, int initialise,
-                          uint32_t* __restrict__ list, unsigned* __restrict__ ctl ) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( v < 4 ) ctl[v] = 0;
-  if ( v >= V ) return;
-  list[v] = kNoEntry;
-  const uint32_t s = voxStart[v], c = voxCount[v];
-  uint8_t edge = st.edge[v];
-  bool    dirty = st.dirty[v] != 0;
-  if ( initialise ) {
-    edge  = ( uint8_t( c ) == 1 ) ? S_DIRECT_EDGE : M_DIRECT_EDGE;
-    dirty = true;
-  } else if ( st.mark[v] && edge == NO_EDGE ) {
-    edge = INDIRECT_EDGE;
-  }
-  if ( dirty ) {  // (only a relabelled voxel has a new histogram: the others keep their row)
-    uint16_t sc[6] = {0, 0, 0, 0, 0, 0};
-    for ( uint32_t j = 0; j < c; ++j ) ++sc[partition[idsSorted[s + j]]];
-#pragma unroll
-    for ( int k = 0; k < 6; ++k ) st.score[size_t( v ) * 8 + k] = sc[k];
-    if ( edge != S_DIRECT_EDGE ) {
-      int used = 0;
-#pragma unroll
-      for ( int k = 0; k < 6; ++k ) used += sc[k] != 0;
-      edge = used == 1 ? NO_EDGE : M_DIRECT_EDGE;
+// recount histogram; apply INDIRECT marks; re-derive class/PPI for dirty voxels (updateScores); then the work list of the NEXT
+// sweep: the voxels that are edge voxels at its start. `list` / `ctl` are the next sweep's (all entries at the "not written yet"
+// sentinel, control words 0: the sweep kernel before this launch reset them, see kSweep).
+__global__ void kRecountAndActivate( VoxState st, const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
+                                     const uint32_t* __restrict__ idsSorted, const uint8_t* __restrict__ partition, int V, int initialise,
+                                     uint32_t* __restrict__ list, unsigned* __restrict__ ctl ) {
+  const int v  = blockIdx.x * blockDim.x + threadIdx.x;
+  bool      on = false;
+  if ( v < V ) {
+    const uint32_t s = voxStart[v], c = voxCount[v];
+    uint8_t edge = st.edge[v];
+    bool    dirty = st.dirty[v] != 0;
+    if ( initialise ) {
+      edge  = ( uint8_t( c ) == 1 ) ? S_DIRECT_EDGE : M_DIRECT_EDGE;
+      dirty = true;
+    } else if ( st.mark[v] && edge == NO_EDGE ) {
+      edge = INDIRECT_EDGE;
     }
-    int best = 0;
+    if ( dirty ) {  // (only a relabelled voxel has a new histogram: the others keep their row)
+      uint16_t sc[6] = {0, 0, 0, 0, 0, 0};
+      for ( uint32_t j = 0; j < c; ++j ) ++sc[partition[idsSorted[s + j]]];
 #pragma unroll
-    for ( int k = 1; k < 6; ++k )
-      if ( sc[k] > sc[best] ) best = k;
-    st.ppi[v] = uint8_t( best );
-  }
-  st.edge[v]   = edge;
-  st.dirty[v]  = 0;
-  st.mark[v]   = 0;
-  st.active[v] = 0;
-}
-
-// initial work list of a sweep: voxels that are edge voxels at sweep start
-__global__ void kInitialActive( VoxState st, int V, uint32_t* __restrict__ list, unsigned* __restrict__ count, int staticPhase ) {
-  const int  v   = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool on  = v < V && st.edge[v] != NO_EDGE;
-  const unsigned m = __ballot_sync( 0xffffffffu, on );
-  unsigned   base = 0;
-  if ( ( threadIdx.x & 31 ) == 0 && m ) {
-    base = atomicAdd( count, __popc( m ) );
-    if ( staticPhase ) {  // count[3] = length of the initial list, count[1] = first ticket of the entries appended later
-      atomicAdd( count + 3, __popc( m ) );
-      atomicAdd( count + 1, __popc( m ) );
+      for ( int k = 0; k < 6; ++k ) st.score[size_t( v ) * 8 + k] = sc[k];
+      if ( edge != S_DIRECT_EDGE ) {
+        int used = 0;
+#pragma unroll
+        for ( int k = 0; k < 6; ++k ) used += sc[k] != 0;
+        edge = used == 1 ? NO_EDGE : M_DIRECT_EDGE;
+      }
+      int best = 0;
+#pragma unroll
+      for ( int k = 1; k < 6; ++k )
+        if ( sc[k] > sc[best] ) best = k;
+      st.ppi[v] = uint8_t( best );
     }
+    st.edge[v]   = edge;
+    st.dirty[v]  = 0;
+    st.mark[v]   = 0;
+    on           = edge != NO_EDGE;
+    st.active[v] = on ? 1 : 0;
   }
+  const unsigned m    = __ballot_sync( 0xffffffffu, on );
+  unsigned       base = 0;
+  if ( ( threadIdx.x & 31 ) == 0 && m ) base = atomicAdd( ctl, __popc( m ) );
   base = __shfl_sync( 0xffffffffu, base, 0 );
-  if ( on ) {
-    st.active[v]                                              = 1;
-    list[base + __popc( m & ( ( 1u << ( threadIdx.x & 31 ) ) - 1 ) )] = v;
-  }
+  if ( on ) list[base + __popc( m & ( ( 1u << ( threadIdx.x & 31 ) ) - 1 ) )] = v;
 }
 
-// smooth[v] = sum of neighbour histograms (uint16 wrap-around like ScoresVector_t), top = first arg-max; then the 2nd voxel
-// classification: mark NO_EDGE neighbours whose PPI differs, and activate those with a larger index for this very sweep.
-// ONE launch per sweep: a persistent kernel over a growing work list. ctl[0] = entries reserved (kInitialActive's + those
-// activated here), ctl[1] = next ticket, ctl[2] = entries finished. A warp takes a ticket, waits until that list slot is written
-// (or until every reserved entry is finished: nothing can be appended any more) and processes it; the result does not depend on
-// the processing order (a voxel is only ever activated by a smaller index, smoothing reads sweep-constant scores).
+// relabel the points of one processed voxel (one warp per voxel, one lane per point); s = its smoothed histogram
+__device__ __forceinline__ void relabelVoxel( VoxState st, uint32_t v, int lane, const uint32_t s[6], const double* __restrict__ weight,
+                                              const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
+                                              const uint32_t* __restrict__ idsSorted, const double* __restrict__ normals, uint8_t* __restrict__ partition ) {
+  uint8_t edgeHere = st.edge[v];
+  if ( edgeHere == NO_EDGE ) edgeHere = INDIRECT_EDGE;  // activated during this sweep
+  if ( edgeHere != M_DIRECT_EDGE ) {
+    int used = 0;
+#pragma unroll
+    for ( int k = 0; k < 6; ++k ) used += s[k] != 0;
+    if ( used == 1 && s[st.ppi[v]] > 0 ) return;
+  }
+  const double   wv = weight[v];
+  const uint32_t st0 = voxStart[v], c = voxCount[v];
+  for ( uint32_t j = lane; j < c; j += 32 ) {
+    const uint32_t p = idsSorted[st0 + j];
+    const double   x = normals[3 * size_t( p )], y = normals[3 * size_t( p ) + 1], z = normals[3 * size_t( p ) + 2];
+    const double   d[6] = {x * 1.0 + y * 0.0 + z * 0.0,  x * 0.0 + y * 1.0 + z * 0.0,  x * 0.0 + y * 0.0 + z * 1.0,
+                           x * -1.0 + y * 0.0 + z * 0.0, x * 0.0 + y * -1.0 + z * 0.0, x * 0.0 + y * 0.0 + z * -1.0};
+    int            best = 0;
+    double         bs   = d[0] + wv * double( uint16_t( s[0] ) );
+#pragma unroll
+    for ( int k = 1; k < 6; ++k ) {
+      const double sc = d[k] + wv * double( uint16_t( s[k] ) );
+      if ( sc > bs ) bs = sc, best = k;
+    }
+    partition[p] = uint8_t( best );
+  }
+  if ( lane == 0 ) st.dirty[v] = 1;
+}
+
+// ONE launch per sweep: a persistent kernel over a growing work list. Per voxel of the list (one warp each):
+//   smooth = sum of the neighbours' histograms (uint16 wrap-around like ScoresVector_t), top = first arg-max; the 2nd voxel
+//   classification: NO_EDGE neighbours whose PPI differs are marked, and those with a larger index join this very sweep; then the
+//   voxel's points are relabelled (argmax of n.o_k + w_v * smooth_k) - scores, classes and PPIs are frozen during a sweep (the
+//   next launch recounts), so relabelling inside the sweep changes nothing another warp reads.
+// ctl[0] = entries reserved (the initial list + those activated here), ctl[1] = next ticket, ctl[2] = entries finished. A warp
+// takes a ticket, waits until that list slot is written (or until every reserved entry is finished: nothing can be appended
+// any more) and processes it; the result does not depend on the processing order (a voxel is only ever activated by a smaller
+// index, smoothing reads sweep-constant scores). Only warps that hold a ticket wait, and tickets are only held by running warps:
+// no dependence on CTAs that are not resident yet.
+// The kernel also resets the OTHER list / control block (the next sweep's, filled by kRecountAndActivate after this launch).
 __device__ __forceinline__ unsigned ldVolatile( const unsigned* p ) { return *reinterpret_cast<const volatile unsigned*>( p ); }
 __global__ void __launch_bounds__( 128 )
-    kSmoothAndMark( VoxState st, uint32_t* __restrict__ list, unsigned* __restrict__ ctl, const uint32_t* __restrict__ adjOff,
-                    const uint32_t* __restrict__ adjLen, const uint32_t* __restrict__ adjData, const uint32_t* __restrict__ nearData,
-                    const uint8_t* __restrict__ nearLen, uint16_t* __restrict__ smooth, unsigned maxSleepNs, int staticPhase ) {
+    kSweep( VoxState st, uint32_t* __restrict__ list, unsigned* __restrict__ ctl, uint32_t* __restrict__ nextList, unsigned* __restrict__ nextCtl, int V,
+            const uint32_t* __restrict__ adjOff, const uint32_t* __restrict__ adjLen, const uint32_t* __restrict__ adjData,
+            const uint32_t* __restrict__ nearData, const uint8_t* __restrict__ nearLen, const double* __restrict__ weight,
+            const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount, const uint32_t* __restrict__ idsSorted,
+            const double* __restrict__ normals, uint8_t* __restrict__ partition, unsigned maxSleepNs ) {
   const int lane = threadIdx.x & 31;
-  // Static phase (optional): the entries kInitialActive wrote (complete before this launch) are dealt out by warp index - no
-  // ticket and no "finished" atomic per voxel on two words every warp of the grid hammers; tickets are only drawn for the
-  // entries appended during the sweep.
-  unsigned       nextStatic = staticPhase ? ( blockIdx.x * blockDim.x + threadIdx.x ) / 32 : 0u;
-  const unsigned nWarps = gridDim.x * ( blockDim.x / 32 ), initial = staticPhase ? ctl[3] : 0u;
-  unsigned       staticDone = 0;
+  for ( int j = blockIdx.x * blockDim.x + threadIdx.x; j < V; j += gridDim.x * blockDim.x ) nextList[j] = kNoEntry;
+  if ( blockIdx.x == 0 && threadIdx.x < 4 ) nextCtl[threadIdx.x] = 0;
   for ( ;; ) {
     unsigned w = 0;
     uint32_t v = kNoEntry;
-    const bool fromStatic = nextStatic < initial;
-    if ( fromStatic ) {
-      v = list[nextStatic];
-      nextStatic += nWarps;
-    } else {
-      if ( staticDone ) {  // this warp's share of the initial list is finished: publish it once
-        __threadfence();
-        if ( lane == 0 ) atomicAdd( &ctl[2], staticDone );
-        staticDone = 0;
-      }
-      if ( lane == 0 ) w = atomicAdd( &ctl[1], 1u );
-      w = __shfl_sync( 0xffffffffu, w, 0 );
-    }
-    if ( !fromStatic && lane == 0 ) {
+    if ( lane == 0 ) {
+      w            = atomicAdd( &ctl[1], 1u );
       unsigned nap = 128;  // (the waiters poll L2: back off, the other frames' kernels share it)
       for ( ;; ) {
         const unsigned c0 = ldVolatile( &ctl[0] );
@@ -355,7 +364,6 @@ __global__ void __launch_bounds__( 128 )
 #pragma unroll
     for ( int k = 1; k < 6; ++k )
       if ( s[k] > s[top] ) top = k;
-    if ( lane < 6 ) smooth[size_t( v ) * 8 + lane] = uint16_t( s[lane] );
     if ( lane < nearLen[v] ) {
       const uint32_t o = nearData[size_t( v ) * kMaxNear + lane];
       if ( st.edge[o] == NO_EDGE && st.ppi[o] != top ) {
@@ -372,57 +380,11 @@ __global__ void __launch_bounds__( 128 )
         }
       }
     }
+    relabelVoxel( st, v, lane, s, weight, voxStart, voxCount, idsSorted, normals, partition );
     __threadfence();  // the entries appended above are reserved (and written) before this one counts as finished
     __syncwarp();
-    if ( fromStatic )
-      ++staticDone;
-    else if ( lane == 0 )
-      atomicAdd( &ctl[2], 1u );
+    if ( lane == 0 ) atomicAdd( &ctl[2], 1u );
   }
-}
-
-// relabel the points of one processed voxel (one warp per voxel, one lane per point)
-__device__ __forceinline__ void relabelVoxel( VoxState st, uint32_t v, int lane, const uint16_t* __restrict__ smooth,
-              const double* __restrict__ weight, const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
-              const uint32_t* __restrict__ idsSorted, const double* __restrict__ normals, uint8_t* __restrict__ partition ) {
-  uint8_t        edgeHere = st.edge[v];
-  if ( edgeHere == NO_EDGE ) edgeHere = INDIRECT_EDGE;  // activated during this sweep
-  uint16_t s[6];
-#pragma unroll
-  for ( int k = 0; k < 6; ++k ) s[k] = smooth[size_t( v ) * 8 + k];
-  if ( edgeHere != M_DIRECT_EDGE ) {
-    int used = 0;
-#pragma unroll
-    for ( int k = 0; k < 6; ++k ) used += s[k] != 0;
-    if ( used == 1 && s[st.ppi[v]] > 0 ) return;
-  }
-  const double   wv = weight[v];
-  const uint32_t st0 = voxStart[v], c = voxCount[v];
-  for ( uint32_t j = lane; j < c; j += 32 ) {
-    const uint32_t p = idsSorted[st0 + j];
-    const double   x = normals[3 * size_t( p )], y = normals[3 * size_t( p ) + 1], z = normals[3 * size_t( p ) + 2];
-    const double   d[6] = {x * 1.0 + y * 0.0 + z * 0.0,  x * 0.0 + y * 1.0 + z * 0.0,  x * 0.0 + y * 0.0 + z * 1.0,
-                           x * -1.0 + y * 0.0 + z * 0.0, x * 0.0 + y * -1.0 + z * 0.0, x * 0.0 + y * 0.0 + z * -1.0};
-    int            best = 0;
-    double         bs   = d[0] + wv * double( s[0] );
-#pragma unroll
-    for ( int k = 1; k < 6; ++k ) {
-      const double sc = d[k] + wv * double( s[k] );
-      if ( sc > bs ) bs = sc, best = k;
-    }
-    partition[p] = uint8_t( best );
-  }
-  if ( lane == 0 ) st.dirty[v] = 1;
-}
-
-// every voxel of the sweep's work list (its length is read on the device)
-__global__ void __launch_bounds__( 128 )
-    kRelabel( VoxState st, const uint32_t* __restrict__ list, const unsigned* __restrict__ ctl, const uint16_t* __restrict__ smooth,
-              const double* __restrict__ weight, const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
-              const uint32_t* __restrict__ idsSorted, const double* __restrict__ normals, uint8_t* __restrict__ partition ) {
-  const int      lane  = threadIdx.x & 31;
-  const unsigned total = ctl[0], nWarps = gridDim.x * ( blockDim.x / 32 );
-  for ( unsigned w = ( blockIdx.x * blockDim.x + threadIdx.x ) / 32; w < total; w += nWarps ) relabelVoxel( st, list[w], lane, smooth, weight, voxStart, voxCount, idsSorted, normals, partition );
 }
 
 std::vector<int> makeOffsets( int r2 ) {
@@ -530,36 +492,36 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
   }
   // ---- voxel state + sweeps
   sc.score.reserve( size_t( V ) * 8 ), sc.smooth.reserve( size_t( V ) * 8 ), sc.edge.reserve( V + 4 ), sc.ppi.reserve( V + 4 );
-  sc.dirty.reserve( V + 4 ), sc.mark.reserve( V + 4 ), sc.active.reserve( V + 8 ), sc.list.reserve( V ), sc.count.reserve( 4 );
+  sc.dirty.reserve( V + 4 ), sc.mark.reserve( V + 4 ), sc.active.reserve( V + 8 );
   PCC_CUDA( cudaMemsetAsync( sc.score, 0, size_t( V ) * 8 * sizeof( uint16_t ), s ) );
   PCC_CUDA( cudaMemsetAsync( sc.active, 0, V + 8, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.edge, 0, V, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.mark, 0, V, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.dirty, 0, V, s ) );
   VoxState st{ sc.score, sc.edge, sc.ppi, sc.dirty, sc.mark, sc.active };
-  sc.count.reserve( 4 );
-  unsigned* const ctl = sc.count;
-  kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 1, sc.list, ctl );
-  // Four launches per sweep and no host round trip: the sweep's work list lives on the device (see kSmoothAndMark).
+  // Two launches per sweep and no host round trip: the sweep's work list lives on the device (see kSweep); two lists / control
+  // blocks alternate, so that the recount at the end of a sweep can fill the next sweep's list.
+  sc.list.reserve( 2 * size_t( V ) ), sc.count.reserve( 8 );
+  uint32_t* lists[2] = { sc.list.p, sc.list.p + V };
+  unsigned* ctls[2]  = { sc.count.p, sc.count.p + 4 };
+  PCC_CUDA( cudaMemsetAsync( sc.list, 0xff, 2 * size_t( V ) * sizeof( uint32_t ), s ) );
+  PCC_CUDA( cudaMemsetAsync( sc.count, 0, 8 * sizeof( unsigned ), s ) );
+  kRecountAndActivate<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 1, lists[0], ctls[0] );
   const int iterations = std::max( 1, prm.iteration_count_refine );
   static const int ctasPerSm = [] {  // (tuning knob; 4 x 128 threads per SM leaves room for the other frames' kernels)
     const char* e = getenv( "PCCB200_SWEEP_CTAS_PER_SM" );
     return e && atoi( e ) > 0 ? atoi( e ) : 4;
   }();
   const int sweepCtas  = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * ctasPerSm ) );
-  static const int staticPhase = [] {  // (experimental, off by default: see kSmoothAndMark)
-    const char* e = getenv( "PCCB200_SWEEP_STATIC" );
-    return e && e[0] == '1' ? 1 : 0;
-  }();
   static const unsigned maxSleepNs = [] {
     const char* e = getenv( "PCCB200_SWEEP_MAX_SLEEP_NS" );
     return unsigned( e && atoi( e ) > 0 ? atoi( e ) : 2048 );
   }();
   for ( int it = 0; it < iterations; ++it ) {
-    kInitialActive<<<divUp( V, 256 ), 256, 0, s>>>( st, V, sc.list, ctl, staticPhase );
-    kSmoothAndMark<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.smooth, maxSleepNs, staticPhase );
-    kRelabel<<<sweepCtas, 128, 0, s>>>( st, sc.list, ctl, sc.smooth, sc.weight, sc.voxStart, sc.voxCount, sc.idsSorted, normals, partition );
-    kRecount<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 0, sc.list, ctl );
+    const int a = it & 1, b = a ^ 1;
+    kSweep<<<sweepCtas, 128, 0, s>>>( st, lists[a], ctls[a], lists[b], ctls[b], V, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.weight,
+                                      sc.voxStart, sc.voxCount, sc.idsSorted, normals, partition, maxSleepNs );
+    kRecountAndActivate<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 0, lists[b], ctls[b] );
     PCC_LAUNCH_CHECK();
   }
 }

@@ -97,7 +97,7 @@ struct ReconScratch {  // the reconstructed cloud (a product: stays with the fra
   size_t           numPoints = 0;
 };
 struct AttrTemp {
-  DevBuf<ushort4>               T[2], tmp;
+  DevBuf<ushort4>               T[2], tmp, tmp2;
   DevBuf<uint8_t>               occ;
   std::vector<DevBuf<ushort4>>  mip;
   std::vector<DevBuf<uint8_t>>  mipOcc;

@@ -1827,8 +1827,16 @@ void* pcco_encode_gof_canvas( int nframes, const int16_t* const* xyz, const uint
       for ( int k = 0; k < 3; ++k ) std::copy( T[map].c[k].begin(), T[map].c[k].end(), F.attrRaw[map].begin() + k * W * H );
     }
     // ---- a26 push-pull background fill with the block-precision occupancy
+    for ( int map = 0; map < 2; ++map ) pushPull( T[map], occ );
+    // group dilation of the attribute maps (PCCEncoder.cpp:391-413, CTC: two maps in one stream, groupDilation on): where the
+    // block-precision occupancy is empty, T0 = T1 = rounded mean of their 8-bit values
+    for ( size_t q = 0; q < size_t( W ) * H; ++q )
+      if ( !occ[q] )
+        for ( int k = 0; k < 3; ++k ) {
+          const uint32_t mean = ( uint32_t( uint8_t( T[0].c[k][q] ) ) + uint32_t( uint8_t( T[1].c[k][q] ) ) + 1 ) >> 1;
+          T[0].c[k][q] = T[1].c[k][q] = uint8_t( mean );
+        }
     for ( int map = 0; map < 2; ++map ) {
-      pushPull( T[map], occ );
       F.attr[map].resize( 3 * W * H );
       for ( int k = 0; k < 3; ++k ) std::copy( T[map].c[k].begin(), T[map].c[k].end(), F.attr[map].begin() + k * W * H );
       rgbToYuv420( F.attr[map], W, H, F.attrYuv[map] );

@@ -638,6 +638,25 @@ void* ref_encode_gof( int nframes, const int16_t* const* xyz, const uint8_t* con
       } else {
         for ( int f = 0; f < nframes; ++f )
           for ( int m = 0; m < 2; ++m ) enc.dilateSmoothedPushPull( frames[f].getTitleFrameContext(), video.getFrame( 2 * f + m ) );  // :367
+        // Group dilation of the two attribute maps (PCCEncoder.cpp:391-413). The reference has this loop inline in encode(), not
+        // as a member that could be called, so it is applied here to the reference's own images: where the (block-precision)
+        // occupancy map is empty both maps take the rounded mean of their 8-bit values.
+        if ( enc.params_.mapCountMinus1_ > 0 && !enc.params_.multipleStreams_ && enc.params_.groupDilation_ ) {
+          for ( int f = 0; f < nframes; ++f ) {
+            auto&        tile = frames[f].getTitleFrameContext();
+            auto&        occ  = tile.getOccupancyMap();
+            const size_t w = tile.getWidth(), h = tile.getHeight();
+            auto &       t0img = video.getFrame( 2 * f ), &t1img = video.getFrame( 2 * f + 1 );
+            for ( size_t y = 0; y < h; ++y )
+              for ( size_t x = 0; x < w; ++x ) {
+                if ( occ[y * w + x] != 0 ) continue;
+                for ( size_t c = 0; c < 3; ++c ) {
+                  const uint32_t mean = ( uint32_t( uint8_t( t0img.getValue( c, x, y ) ) ) + uint32_t( uint8_t( t1img.getValue( c, x, y ) ) ) + 1 ) >> 1;
+                  t0img.setValue( c, x, y, uint8_t( mean ) ), t1img.setValue( c, x, y, uint8_t( mean ) );
+                }
+              }
+          }
+        }
       }
       G->seconds[6] = secs( t0 );
       for ( int f = 0; f < nframes; ++f )

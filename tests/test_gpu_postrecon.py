@@ -1,7 +1,7 @@
-"""PARKED (not collected: the file name does not match test_*.py). GPU checks of the experimental post-reconstruction kernels
-(csrc/postrecon.cu, entry points pccb200x_*) against the oracle. Round 1 ended without GPU minutes, so these have not run yet;
-next round:   python -m pytest tests/gpu_pending_postrecon.py -m gpu -x -q
-and, once green, rename to test_gpu_postrecon.py and declare the entry points in include/pccb200.h."""
+"""GPU parity of the post-reconstruction chain (csrc/postrecon.cu, entry points declared in include/pccb200.h) against
+the oracle, which is pinned against the reference on the CPU (tests/test_smoothing_oracle.py); the decoder-side binding
+(integration/pccb200_shim.cpp decodeFrame) against the reference's own generatePointCloud; and the random-cloud fuzz of
+tests/test_oracle_fuzz.py with the product in place of the oracle."""
 import ctypes as C
 
 import numpy as np
@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 def test_gpu_geometry_smoothing_vs_oracle(grid, threshold, oracle, product):
     frames = [synth.figure(scale=0.15, seed=9, frame=0), synth.double_sheet(n_side=48, seed=5)]
     prm = bindings.ctc_seg_params(bits=10, iterations=4, weight=oracle.weight_normal(frames[0][0], 11))
-    fn = product.lib.pccb200x_smooth_geometry
+    fn = product.lib.pccb200_smooth_geometry
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double]
     for fr in oracle.encode_gof(frames, prm, stop_after=3):
         xyz, bnd, part = fr.data[6].reshape(-1, 3), fr.data[9], fr.data[8]
@@ -38,7 +38,7 @@ def test_gpu_colour_conversions_vs_oracle(oracle, product):
     f.restype, f.argtypes = None, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
     f(y.ctypes.data_as(C.c_void_p), W, H, want.ctypes.data_as(C.c_void_p))
     got = np.zeros_like(want)
-    g = product.lib.pccb200x_yuv420_to_yuv444_16
+    g = product.lib.pccb200_yuv420_to_yuv444_16
     g.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
     assert g(product.ctx, y.ctypes.data_as(C.c_void_p), W, H, got.ctypes.data_as(C.c_void_p)) == 0
     assert np.array_equal(got, want)
@@ -48,7 +48,7 @@ def test_gpu_colour_conversions_vs_oracle(oracle, product):
     f.restype, f.argtypes = None, [C.c_void_p, C.c_size_t, C.c_void_p]
     f(yuv.ctypes.data_as(C.c_void_p), len(yuv), want.ctypes.data_as(C.c_void_p))
     got = np.zeros_like(want)
-    g = product.lib.pccb200x_yuv16_to_rgb8
+    g = product.lib.pccb200_yuv16_to_rgb8
     g.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     assert g(product.ctx, yuv.ctypes.data_as(C.c_void_p), len(yuv), got.ctypes.data_as(C.c_void_p)) == 0
     assert np.array_equal(got, want)
@@ -64,7 +64,7 @@ def test_gpu_colour_transfer_onto_smoothed_cloud_vs_oracle(spread, oracle, produ
     col16 = (fr.data[10].reshape(-1, 3).astype(np.uint16) * spread + 11).astype(np.uint16)
     sm_xyz, sm_bnd = smooth(oracle.lib._dll, "pcco_smooth_geometry", xyz, bnd, part, 8, 64.0)
     want = transfer(oracle.lib._dll, "pcco_transfer_colors16_smoothed", xyz, col16, sm_xyz, col16, sm_bnd)
-    fn = product.lib.pccb200x_transfer_colors16_smoothed
+    fn = product.lib.pccb200_transfer_colors16_smoothed
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     sx, sc = np.ascontiguousarray(xyz, np.int16), np.ascontiguousarray(col16)
     tx, tc, tb = np.ascontiguousarray(sm_xyz, np.int16), col16.copy(), np.ascontiguousarray(sm_bnd, np.uint16)
