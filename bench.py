@@ -465,6 +465,8 @@ def main():
         t = torch.tensor([e2e_t, dev_t, wall_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t, dev_t, wall_total = (float(x) for x in t)
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     pts_all = total_pts * world * args.steps

@@ -143,6 +143,61 @@ __global__ void __launch_bounds__( 128 )
   if ( ch ) *changed = 1;
 }
 
+// The same propagation on a compact list of the edges that can still carry a label: after the contraction only the one-way
+// links between DIFFERENT sets matter (about a tenth of the 16 n neighbour slots). Built once per outer iteration, then every
+// round is a pass over that list instead of over all neighbour rows.
+__global__ void __launch_bounds__( 128 )
+    kCrossEdges( const uint32_t* __restrict__ nbr, const uint8_t* __restrict__ raw, const uint8_t* __restrict__ partition,
+                 const uint32_t* __restrict__ parent, int n, int k, uint2* __restrict__ edges, unsigned* __restrict__ count, unsigned capacity ) {
+  const int i    = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t  to[16];
+  int       c = 0;
+  uint32_t  ri = 0;
+  if ( i < n && raw[i] ) {
+    ri               = parent[i];
+    const uint8_t pi = partition[i];
+    for ( int t = 0; t < k && t < 16; ++t ) {
+      const uint32_t j = nbr[size_t( i ) * k + t];
+      if ( j == kInf ) break;
+      if ( !raw[j] || partition[j] != pi ) continue;
+      const uint32_t rj = parent[j];
+      if ( rj != ri ) to[c++] = rj;
+    }
+  }
+  // warp-aggregated reservation
+  int inc = c;
+#pragma unroll
+  for ( int o = 1; o < 32; o <<= 1 ) {
+    const int t = __shfl_up_sync( 0xffffffffu, inc, o );
+    if ( lane >= o ) inc += t;
+  }
+  const int total = __shfl_sync( 0xffffffffu, inc, 31 );
+  unsigned  base  = 0;
+  if ( lane == 31 && total ) base = atomicAdd( count, unsigned( total ) );
+  base = __shfl_sync( 0xffffffffu, base, 31 ) + unsigned( inc - c );
+  for ( int e = 0; e < c; ++e )
+    if ( base + e < capacity ) edges[base + e] = make_uint2( ri, to[e] );
+}
+// `rounds` relaxation passes per launch (asynchronous updates are fine: min-label propagation is monotone, every schedule reaches
+// the same fixed point). *changed = 1 when a label moved, 2 when the list did not fit (the caller falls back to kPropagate).
+__global__ void __launch_bounds__( 256 )
+    kPropagateEdges( const uint2* __restrict__ edges, const unsigned* __restrict__ count, unsigned capacity, uint32_t* compLabel, int* changed, int rounds ) {
+  const unsigned E = *count;
+  if ( E > capacity ) {
+    if ( blockIdx.x == 0 && threadIdx.x == 0 ) *changed = 2;
+    return;
+  }
+  bool ch = false;
+  for ( int r = 0; r < rounds; ++r )
+    for ( unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x ) {
+      const uint2    ed = edges[e];
+      const uint32_t li = *reinterpret_cast<volatile uint32_t*>( &compLabel[ed.x] );
+      if ( li != kInf && *reinterpret_cast<volatile uint32_t*>( &compLabel[ed.y] ) > li && atomicMin( &compLabel[ed.y], li ) > li ) ch = true;
+    }
+  if ( ch ) *changed = 1;
+}
+
 __global__ void kLabelAndCount( const uint8_t* __restrict__ raw, const uint32_t* __restrict__ parent, const uint32_t* __restrict__ compLabel,
                                 int n, uint32_t* __restrict__ label, uint32_t* compSize ) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -460,7 +515,7 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
 
   sc.raw.reserve( n ), sc.minD2.reserve( n ), sc.mutual.reserve( n ), sc.parent.reserve( n ), sc.compLabel.reserve( n );
   sc.compSize.reserve( n ), sc.label.reserve( n ), sc.kept.reserve( n + 1 ), sc.keptScan.reserve( n + 1 ), sc.member.reserve( n );
-  sc.scanTmp.reserve( scanTmpElems( n ) ), sc.ints.reserve( 16 );
+  sc.scanTmp.reserve( scanTmpElems( n ) ), sc.ints.reserve( 16 ), sc.keys.reserve( 4 * n );
   PCC_CUDA( cudaMemsetAsync( sc.raw, 1, n, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.minD2, 255, n, s ) );
   kMutual<<<divUp( n, 128 ), 128, 0, s>>>( nbr, N, k, sc.mutual );
@@ -485,13 +540,28 @@ void segmentPatches( PatchScratch& sc, PatchResult& out, const short4* pts, cons
     kIterInit<<<gridN, TB, 0, s>>>( sc.raw, sc.minD2, N, detect, sc.parent, sc.compLabel, sc.compSize );
     kHook<<<divUp( n, 128 ), 128, 0, s>>>( nbr, sc.mutual, sc.raw, partition, N, k, sc.parent );
     kCompressAndSeed<<<gridN, TB, 0, s>>>( sc.parent, sc.raw, N, sc.compLabel );
-    for ( ;; ) {
-      PCC_CUDA( cudaMemsetAsync( sc.ints, 0, sizeof( int ), s ) );
-      for ( int r = 0; r < 4; ++r ) kPropagate<<<divUp( n, 128 ), 128, 0, s>>>( nbr, sc.raw, partition, sc.parent, N, k, sc.compLabel, sc.ints );
-      int changed = 0;
-      PCC_CUDA( cudaMemcpyAsync( &changed, sc.ints, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
-      streamWait( s );
-      if ( !changed ) break;
+    {
+      const unsigned capacity = unsigned( 4 * n );
+      sc.keys.reserve( capacity );  // (the projection's pixel keys are not alive yet: 8 bytes per entry, as an edge)
+      uint2* const edges = reinterpret_cast<uint2*>( sc.keys.p );
+      PCC_CUDA( cudaMemsetAsync( sc.ints.p + 8, 0, sizeof( int ), s ) );
+      kCrossEdges<<<divUp( n, 128 ), 128, 0, s>>>( nbr, sc.raw, partition, sc.parent, N, k, edges, reinterpret_cast<unsigned*>( sc.ints.p + 8 ), capacity );
+      bool fallback = false;
+      for ( ;; ) {
+        PCC_CUDA( cudaMemsetAsync( sc.ints, 0, sizeof( int ), s ) );
+        if ( !fallback )
+          kPropagateEdges<<<148 * 4, 256, 0, s>>>( edges, reinterpret_cast<unsigned*>( sc.ints.p + 8 ), capacity, sc.compLabel, sc.ints, 8 );
+        else
+          for ( int r = 0; r < 4; ++r ) kPropagate<<<divUp( n, 128 ), 128, 0, s>>>( nbr, sc.raw, partition, sc.parent, N, k, sc.compLabel, sc.ints );
+        int changed = 0;
+        PCC_CUDA( cudaMemcpyAsync( &changed, sc.ints, sizeof( int ), cudaMemcpyDeviceToHost, s ) );
+        streamWait( s );
+        if ( changed == 2 ) {
+          fallback = true;
+          continue;
+        }
+        if ( !changed ) break;
+      }
     }
     kLabelAndCount<<<gridN, TB, 0, s>>>( sc.raw, sc.parent, sc.compLabel, N, sc.label, sc.compSize );
     kKeptFlags<<<gridN, TB, 0, s>>>( sc.compSize, N, uint32_t( prm.min_point_count_per_cc ), sc.kept );

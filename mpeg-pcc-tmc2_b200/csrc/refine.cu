@@ -233,14 +233,15 @@ struct VoxState {
 };
 
 // recount histogram; apply INDIRECT marks; re-derive class/PPI for dirty voxels (updateScores); then the work list of the NEXT
-// sweep: the voxels that are edge voxels at its start. `list` / `ctl` are the next sweep's (all entries at the "not written yet"
-// sentinel, control words 0: the sweep kernel before this launch reset them, see kSweep).
+// sweep: the voxels that are edge voxels at its start. `list` / `ctl` are the next sweep's (counter 0: kSweepStatic cleared it).
 __global__ void kRecountAndActivate( VoxState st, const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
                                      const uint32_t* __restrict__ idsSorted, const uint8_t* __restrict__ partition, int V, int initialise,
-                                     uint32_t* __restrict__ list, unsigned* __restrict__ ctl ) {
+                                     uint32_t* __restrict__ list, unsigned* __restrict__ ctl, uint32_t* __restrict__ tail, unsigned* __restrict__ tailCtl ) {
   const int v  = blockIdx.x * blockDim.x + threadIdx.x;
   bool      on = false;
+  if ( v < 4 ) tailCtl[v] = 0;
   if ( v < V ) {
+    tail[v]          = kNoEntry;  // (the tail list of the sweep that just ended is dead: reset for the next one)
     const uint32_t s = voxStart[v], c = voxCount[v];
     uint8_t edge = st.edge[v];
     bool    dirty = st.dirty[v] != 0;
@@ -311,37 +312,80 @@ __device__ __forceinline__ void relabelVoxel( VoxState st, uint32_t v, int lane,
   if ( lane == 0 ) st.dirty[v] = 1;
 }
 
-// ONE launch per sweep: a persistent kernel over a growing work list. Per voxel of the list (one warp each):
-//   smooth = sum of the neighbours' histograms (uint16 wrap-around like ScoresVector_t), top = first arg-max; the 2nd voxel
-//   classification: NO_EDGE neighbours whose PPI differs are marked, and those with a larger index join this very sweep; then the
-//   voxel's points are relabelled (argmax of n.o_k + w_v * smooth_k) - scores, classes and PPIs are frozen during a sweep (the
-//   next launch recounts), so relabelling inside the sweep changes nothing another warp reads.
-// ctl[0] = entries reserved (the initial list + those activated here), ctl[1] = next ticket, ctl[2] = entries finished. A warp
-// takes a ticket, waits until that list slot is written (or until every reserved entry is finished: nothing can be appended
-// any more) and processes it; the result does not depend on the processing order (a voxel is only ever activated by a smaller
-// index, smoothing reads sweep-constant scores). Only warps that hold a ticket wait, and tickets are only held by running warps:
-// no dependence on CTAs that are not resident yet.
-// The kernel also resets the OTHER list / control block (the next sweep's, filled by kRecountAndActivate after this launch).
+// One voxel of a sweep (one warp): smooth = sum of the neighbours' histograms (uint16 wrap-around like ScoresVector_t), top = first
+// arg-max; the 2nd voxel classification: NO_EDGE neighbours whose PPI differs are marked, and those with a larger index join this
+// very sweep (appended to the TAIL list); then the voxel's points are relabelled (argmax of n.o_k + w_v * smooth_k) - scores,
+// classes and PPIs are frozen during a sweep (the recount launch updates them), so relabelling inside the sweep changes nothing
+// another warp reads, and the result does not depend on the processing order (a voxel is only ever activated by a smaller index).
+struct SweepData {
+  VoxState        st;
+  const uint32_t *adjOff, *adjLen, *adjData, *nearData;
+  const uint8_t*  nearLen;
+  const double*   weight;
+  const uint32_t *voxStart, *voxCount, *idsSorted;
+  const double*   normals;
+  uint8_t*        partition;
+  uint32_t*       tail;     // voxels activated during the sweep
+  unsigned*       tailCtl;  // [0] entries reserved, [1] next ticket, [2] entries finished
+};
+__device__ __forceinline__ void sweepVoxel( const SweepData& d, uint32_t v, int lane ) {
+  const uint32_t off = d.adjOff[v], len = d.adjLen[v];
+  uint32_t       s[6] = {0, 0, 0, 0, 0, 0};
+  for ( uint32_t i = lane; i < len; i += 32 ) {
+    const uint4 r = *reinterpret_cast<const uint4*>( d.st.score + size_t( d.adjData[off + i] ) * 8 );
+    s[0] += r.x & 0xffff, s[1] += r.x >> 16, s[2] += r.y & 0xffff, s[3] += r.y >> 16, s[4] += r.z & 0xffff, s[5] += r.z >> 16;
+  }
+#pragma unroll
+  for ( int k = 0; k < 6; ++k ) s[k] = __reduce_add_sync( 0xffffffffu, s[k] ) & 0xffffu;
+  int top = 0;
+#pragma unroll
+  for ( int k = 1; k < 6; ++k )
+    if ( s[k] > s[top] ) top = k;
+  if ( lane < d.nearLen[v] ) {
+    const uint32_t o = d.nearData[size_t( v ) * kMaxNear + lane];
+    if ( d.st.edge[o] == NO_EDGE && d.st.ppi[o] != top ) {
+      d.st.mark[o] = 1;
+      if ( o > v ) {
+        // byte-granular test-and-set on the active flags
+        unsigned*      word = reinterpret_cast<unsigned*>( d.st.active ) + ( o >> 2 );
+        const unsigned bit  = 1u << ( 8 * ( o & 3 ) );
+        const unsigned old  = atomicOr( word, bit );
+        if ( !( old & bit ) ) {
+          const unsigned at = atomicAdd( &d.tailCtl[0], 1u );
+          *reinterpret_cast<volatile uint32_t*>( &d.tail[at] ) = o;
+        }
+      }
+    }
+  }
+  relabelVoxel( d.st, v, lane, s, d.weight, d.voxStart, d.voxCount, d.idsSorted, d.normals, d.partition );
+}
+
+// Sweep, launch 1 of 3: the voxels that are edge voxels at sweep start (the list kRecountAndActivate left, complete before this
+// launch) are dealt out by warp index - no tickets, no polling. Also clears the OTHER initial list's counter (the next sweep's).
+__global__ void __launch_bounds__( 128 ) kSweepStatic( SweepData d, const uint32_t* __restrict__ list, const unsigned* __restrict__ ctl, unsigned* __restrict__ nextCtl ) {
+  const int      lane  = threadIdx.x & 31;
+  const unsigned count = ctl[0], nWarps = gridDim.x * ( blockDim.x / 32 );
+  if ( blockIdx.x == 0 && threadIdx.x == 0 ) nextCtl[0] = 0;
+  for ( unsigned w = ( blockIdx.x * blockDim.x + threadIdx.x ) / 32; w < count; w += nWarps ) sweepVoxel( d, list[w], lane );
+}
+
+// Sweep, launch 2 of 3: the voxels activated during the sweep - a persistent kernel over the growing tail list. A warp takes a
+// ticket, waits until that list slot is written (or until every reserved entry is finished: nothing can be appended any more) and
+// processes it. Only warps that hold a ticket wait, and an entry is reserved by a RUNNING warp that writes it at once: no
+// dependence on CTAs that are not resident yet. With an empty tail the first ticket sees "0 reserved, 0 finished" and the kernel ends.
 __device__ __forceinline__ unsigned ldVolatile( const unsigned* p ) { return *reinterpret_cast<const volatile unsigned*>( p ); }
-__global__ void __launch_bounds__( 128 )
-    kSweep( VoxState st, uint32_t* __restrict__ list, unsigned* __restrict__ ctl, uint32_t* __restrict__ nextList, unsigned* __restrict__ nextCtl, int V,
-            const uint32_t* __restrict__ adjOff, const uint32_t* __restrict__ adjLen, const uint32_t* __restrict__ adjData,
-            const uint32_t* __restrict__ nearData, const uint8_t* __restrict__ nearLen, const double* __restrict__ weight,
-            const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount, const uint32_t* __restrict__ idsSorted,
-            const double* __restrict__ normals, uint8_t* __restrict__ partition, unsigned maxSleepNs ) {
+__global__ void __launch_bounds__( 128 ) kSweepTail( SweepData d, unsigned maxSleepNs ) {
   const int lane = threadIdx.x & 31;
-  for ( int j = blockIdx.x * blockDim.x + threadIdx.x; j < V; j += gridDim.x * blockDim.x ) nextList[j] = kNoEntry;
-  if ( blockIdx.x == 0 && threadIdx.x < 4 ) nextCtl[threadIdx.x] = 0;
+  unsigned* ctl  = d.tailCtl;
   for ( ;; ) {
-    unsigned w = 0;
     uint32_t v = kNoEntry;
     if ( lane == 0 ) {
-      w            = atomicAdd( &ctl[1], 1u );
-      unsigned nap = 128;  // (the waiters poll L2: back off, the other frames' kernels share it)
+      const unsigned w   = atomicAdd( &ctl[1], 1u );
+      unsigned       nap = 128;  // (the waiters poll L2: back off, the other frames' kernels share it)
       for ( ;; ) {
         const unsigned c0 = ldVolatile( &ctl[0] );
         if ( w < c0 ) {
-          while ( ( v = ldVolatile( &list[w] ) ) == kNoEntry ) __nanosleep( 20 );
+          while ( ( v = ldVolatile( &d.tail[w] ) ) == kNoEntry ) __nanosleep( 20 );
           break;
         }
         const unsigned done = ldVolatile( &ctl[2] );
@@ -352,35 +396,7 @@ __global__ void __launch_bounds__( 128 )
     }
     v = __shfl_sync( 0xffffffffu, v, 0 );
     if ( v == kNoEntry ) return;
-    const uint32_t off = adjOff[v], len = adjLen[v];
-    uint32_t       s[6] = {0, 0, 0, 0, 0, 0};
-    for ( uint32_t i = lane; i < len; i += 32 ) {
-      const uint4 r = *reinterpret_cast<const uint4*>( st.score + size_t( adjData[off + i] ) * 8 );
-      s[0] += r.x & 0xffff, s[1] += r.x >> 16, s[2] += r.y & 0xffff, s[3] += r.y >> 16, s[4] += r.z & 0xffff, s[5] += r.z >> 16;
-    }
-#pragma unroll
-    for ( int k = 0; k < 6; ++k ) s[k] = __reduce_add_sync( 0xffffffffu, s[k] ) & 0xffffu;
-    int top = 0;
-#pragma unroll
-    for ( int k = 1; k < 6; ++k )
-      if ( s[k] > s[top] ) top = k;
-    if ( lane < nearLen[v] ) {
-      const uint32_t o = nearData[size_t( v ) * kMaxNear + lane];
-      if ( st.edge[o] == NO_EDGE && st.ppi[o] != top ) {
-        st.mark[o] = 1;
-        if ( o > v ) {
-          // byte-granular test-and-set on the active flags
-          unsigned* word = reinterpret_cast<unsigned*>( st.active ) + ( o >> 2 );
-          const unsigned bit = 1u << ( 8 * ( o & 3 ) );
-          const unsigned old = atomicOr( word, bit );
-          if ( !( old & bit ) ) {
-            const unsigned at = atomicAdd( &ctl[0], 1u );
-            *reinterpret_cast<volatile uint32_t*>( &list[at] ) = o;
-          }
-        }
-      }
-    }
-    relabelVoxel( st, v, lane, s, weight, voxStart, voxCount, idsSorted, normals, partition );
+    sweepVoxel( d, v, lane );
     __threadfence();  // the entries appended above are reserved (and written) before this one counts as finished
     __syncwarp();
     if ( lane == 0 ) atomicAdd( &ctl[2], 1u );
@@ -499,29 +515,33 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
   PCC_CUDA( cudaMemsetAsync( sc.mark, 0, V, s ) );
   PCC_CUDA( cudaMemsetAsync( sc.dirty, 0, V, s ) );
   VoxState st{ sc.score, sc.edge, sc.ppi, sc.dirty, sc.mark, sc.active };
-  // Two launches per sweep and no host round trip: the sweep's work list lives on the device (see kSweep); two lists / control
-  // blocks alternate, so that the recount at the end of a sweep can fill the next sweep's list.
-  sc.list.reserve( 2 * size_t( V ) ), sc.count.reserve( 8 );
+  // Three launches per sweep and no host round trip: the initial work list of a sweep is dealt out statically (kSweepStatic), the
+  // voxels activated during the sweep go through a device-side growing list (kSweepTail), the recount fills the next initial list
+  // (two initial lists / counters alternate).
+  sc.list.reserve( 3 * size_t( V ) ), sc.count.reserve( 12 );
   uint32_t* lists[2] = { sc.list.p, sc.list.p + V };
   unsigned* ctls[2]  = { sc.count.p, sc.count.p + 4 };
-  PCC_CUDA( cudaMemsetAsync( sc.list, 0xff, 2 * size_t( V ) * sizeof( uint32_t ), s ) );
-  PCC_CUDA( cudaMemsetAsync( sc.count, 0, 8 * sizeof( unsigned ), s ) );
-  kRecountAndActivate<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 1, lists[0], ctls[0] );
+  uint32_t* tail     = sc.list.p + 2 * size_t( V );
+  unsigned* tailCtl  = sc.count.p + 8;
+  PCC_CUDA( cudaMemsetAsync( sc.count, 0, 12 * sizeof( unsigned ), s ) );
+  kRecountAndActivate<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 1, lists[0], ctls[0], tail, tailCtl );
   const int iterations = std::max( 1, prm.iteration_count_refine );
-  static const int ctasPerSm = [] {  // (tuning knob; 4 x 128 threads per SM leaves room for the other frames' kernels)
+  static const int ctasPerSm = [] {  // (tuning knob of the static part; 8 x 128 threads per SM)
     const char* e = getenv( "PCCB200_SWEEP_CTAS_PER_SM" );
-    return e && atoi( e ) > 0 ? atoi( e ) : 4;
+    return e && atoi( e ) > 0 ? atoi( e ) : 8;
   }();
-  const int sweepCtas  = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * ctasPerSm ) );
+  const int staticCtas = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * ctasPerSm ) );
+  const int tailCtas   = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * 2 ) );
   static const unsigned maxSleepNs = [] {
     const char* e = getenv( "PCCB200_SWEEP_MAX_SLEEP_NS" );
     return unsigned( e && atoi( e ) > 0 ? atoi( e ) : 2048 );
   }();
+  SweepData d{ st, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.weight, sc.voxStart, sc.voxCount, sc.idsSorted, normals, partition, tail, tailCtl };
   for ( int it = 0; it < iterations; ++it ) {
     const int a = it & 1, b = a ^ 1;
-    kSweep<<<sweepCtas, 128, 0, s>>>( st, lists[a], ctls[a], lists[b], ctls[b], V, sc.adjOff, sc.adjLen, sc.adjData, sc.nearData, sc.nearLen, sc.weight,
-                                      sc.voxStart, sc.voxCount, sc.idsSorted, normals, partition, maxSleepNs );
-    kRecountAndActivate<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 0, lists[b], ctls[b] );
+    kSweepStatic<<<staticCtas, 128, 0, s>>>( d, lists[a], ctls[a], ctls[b] );
+    kSweepTail<<<tailCtas, 128, 0, s>>>( d, maxSleepNs );
+    kRecountAndActivate<<<divUp( V, 128 ), 128, 0, s>>>( st, sc.voxStart, sc.voxCount, sc.idsSorted, partition, V, 0, lists[b], ctls[b], tail, tailCtl );
     PCC_LAUNCH_CHECK();
   }
 }
