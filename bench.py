@@ -185,8 +185,9 @@ def config(args, npts, frames_per_rank, world):
                       "packing, occupancy/geometry images + dilation, generatePointCloud, colour transfer, attribute images, push-pull padding",
             "excluded": "ply load, videoEncoder.compress x3, post-processing, bitstream (as in BASELINE.md §4)",
             "frames_in_flight": frames_per_rank * lanes, "gofs_in_flight": lanes, "host_cores": host_cores(),
-            "parallelism": ("frames of a GOF sharded over %d GPU(s), canvas size reduced by NCCL all-reduce(MAX), %d GOFs per collective, off the critical path"
-                            % (world, args.exchange_batch)) if sharded else "whole GOFs per GPU (%d GPU(s)), no collective on the data path" % world,
+            "parallelism": ("frames of a GOF sharded over %d GPU(s), canvas size reduced by NCCL all-reduce(MAX), up to %d GOFs per collective, off the critical path"
+                            % (world, args.exchange_batch)) if sharded else
+                           "frames of a GOF sharded over %d GPU(s) (frame f -> GPU f mod G), one NCCL all-gather of the patch records per GOF, packing replicated" % world,
             "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2",
             "host_buffers": "pinned (inputs and the frames handed to the video codec)",
             "handoff": "occupancy video + geometry D0/D1 luma + attribute T0/T1 converted to 8-bit YUV 4:2:0 on the device (the conversion the reference does inside compress())",
@@ -319,12 +320,12 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
-        if args.condition == "ai":   # the canvas exchange gets its own communicator + high-priority stream
-            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            exchange_group = dist.new_group(backend="nccl", pg_options=opts)
-    sharded = world > 1 and args.condition == "ai"
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # the exchange gets its own communicator + high-priority stream
+        exchange_group = dist.new_group(backend="nccl", pg_options=opts)
+    sharded = world > 1
+    sharded_ra = sharded and args.condition == "ra"
     sys.path.insert(0, os.path.join(ROOT, "mpeg-pcc-tmc2_b200"))
-    from sharding import CanvasExchange
+    from sharding import CanvasExchange, RecordExchange
     frames = make_frames(args.frames, args, seed=rank, pin=True)
     lanes = max(1, min(args.gofs_in_flight, args.steps))          # GOFs in flight: one library context (streams + buffers) each
     prods = [bindings.Product(local) for _ in range(lanes)]
@@ -343,8 +344,12 @@ def main():
     outbuf, outlock = dict(), threading.Lock()   # ONE set of pinned hand-off buffers: the lanes take turns copying out (45 ms per GOF)
 
     def phase_a(lane):
-        """a1..a13 of one GOF: segmentation (incl. the orientation walk) + packing"""
-        return bindings.ProductGof(prods[lane], frames, prm, prec)
+        """a1..a13 of one GOF: segmentation (incl. the orientation walk) + packing (sharded random access: segmentation only)"""
+        return bindings.ProductGof(prods[lane], frames, prm, prec, stop_after=5 if sharded_ra else 1)
+
+    # sharded random access: local frame i of a rank is frame i * world + rank of the GOF (frame f -> GPU f mod G, SURVEY 8e)
+    total_frames = args.frames * world
+    local_of = [(f // world if f % world == rank else -1) for f in range(total_frames)]
 
     def phase_b(g, W, H):
         """a16..a26 + hand-off: images, reconstruction, colour, attribute images; D2H of every frame the codec would receive"""
@@ -386,7 +391,8 @@ def main():
         results = [None] * count
         lock = threading.Lock()
         state = {"next": 0}
-        ex = CanvasExchange(dist, count, batch=args.exchange_batch, group=exchange_group, device=local) if sharded else None
+        ex = CanvasExchange(dist, count, batch=args.exchange_batch, group=exchange_group, device=local) if sharded and not sharded_ra else None
+        rx = RecordExchange(dist, count, total_frames, bindings.PATCH_DTYPE, group=exchange_group, device=local) if sharded_ra else None
 
         def worker(lane):
             torch.cuda.set_device(local)   # (the current device is per thread)
@@ -400,6 +406,13 @@ def main():
                     return
                 t0 = time.perf_counter()
                 gof = phase_a(lane)
+                tw = 0.0
+                if rx is not None:   # ONE exchange of patch records (KBs per frame), then the deterministic packing on every rank
+                    rx.post(g, [(i * world + rank,) + gof.patch_records(i) for i in range(len(frames))])
+                    tx = time.perf_counter()
+                    records = rx.wait(g)
+                    tw = time.perf_counter() - tx
+                    gof.pack_ra(records, local_of)
                 ta = time.perf_counter()
                 W, H = gof.dims(0)[:2]
                 if ex is not None:
@@ -415,7 +428,7 @@ def main():
                 spans = prods[lane].profile_read()
                 gof.free()
                 tf = time.perf_counter()
-                host_phases.append((ta - t0, t1 - ta, t2 - t1, tv - t2, tf - t0))
+                host_phases.append((ta - t0, t1 - ta, t2 - t1, (tv - t2) + tw, tf - t0))
                 gof_log.append((lane, t0, ta, t1, t2, tv, tf))
                 results[g] = (t1 - t0, t2 - t0, spans, nbytes)
 
@@ -424,6 +437,9 @@ def main():
         if ex is not None:
             ex.close()
             xs = (ex.collectives, ex.seconds)
+        if rx is not None:
+            rx.close()
+            xs = (rx.collectives, rx.seconds)
         return results, xs
 
     def barrier():
@@ -518,7 +534,8 @@ def main():
         "gpu_mem_used_gb": round((torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 2**30, 1),
     }
     if xstats is not None:
-        out["canvas_exchange"] = {"collectives": xstats[0], "ms_per_collective": round(xstats[1] / max(1, xstats[0]) * 1e3, 2), "gofs_reformed": stats["reformed"]}
+        out["exchange"] = {"kind": "patch-record all-gather (2 collectives per GOF)" if sharded_ra else "canvas-size all-reduce(MAX)",
+                           "collectives": xstats[0], "ms_per_collective": round(xstats[1] / max(1, xstats[0]) * 1e3, 2), "gofs_reformed": stats["reformed"]}
     counts_path = os.path.join(ROOT, "profiles", "launch_counts.json")
     if os.path.exists(counts_path):
         with open(counts_path) as f:

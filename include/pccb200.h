@@ -156,7 +156,8 @@ void   pccb200_patches_free( pccb200_patchlist* pl );
  * GOF concurrently (one stream per frame). The occupancy/geometry videos are treated as losslessly coded (decoded ==
  * source), which is what the reference sees for occupancy in CTC and what a passthrough codec gives for geometry.
  * params->weight_normal must hold pccb200_weight_normal() of frame 0 (PCCEncoder.cpp:4726).
- * stop_after: 0 = all stages, 1 = after packing, 2 = after the geometry images, 3 = after generatePointCloud.
+ * stop_after: 0 = all stages, 1 = after packing, 2 = after the geometry images, 3 = after generatePointCloud, 5 = after the segmentation
+ * (no packing; random access only: see pccb200_gof_pack_ra).
  * One GOF is live per context: a later pccb200_encode_gof reuses the device buffers of the earlier one. */
 typedef struct pccb200_gof pccb200_gof;
 int  pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
@@ -167,6 +168,20 @@ int  pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xy
  * A rank need not wait for the reduction: it may resume on its local size at once and, should the reduced size turn out larger,
  * call pccb200_gof_resume( gof, W, H, 0 ) again on the finished GOF with the larger canvas (all products are formed anew). */
 int  pccb200_gof_resume( pccb200_gof* gof, size_t width, size_t height, int stop_after );
+/* Multi-GPU, random access (global_patch_allocation = 1): every frame is packed against the previous one
+ * (PCCEncoder::placeSegments, PCCEncoder.cpp:4778-4805) and the global patch allocation iterates over the whole GOF
+ * (performDataAdaptiveGPAMethod, :6838-6970), so a sharded GOF needs ONE exchange of patch metadata. Each rank
+ * calls pccb200_encode_gof with stop_after = 5 (segmentation only), the ranks all-gather the records of pccb200_gof_patches
+ * (pccb200_patches_get with depth = NULL: patch fields + 16-pixel block occupancies, KBs per frame), and every rank calls
+ * pccb200_gof_pack_ra with the records of ALL frames of the GOF in frame order:
+ *   patch_counts[f]     patches of frame f, f = 0 .. total_frames-1
+ *   patches             the frames' records, concatenated; occ_offset relative to the frame's own occupancy block
+ *   occ, occ_sizes[f]   the frames' block occupancies, concatenated / bytes per frame
+ *   local_frame[f]      index of frame f among the frames of `gof`, or -1 when another rank holds it
+ * The packing is deterministic: all ranks compute the same placements, each installs those of its own frames. Afterwards the GOF is
+ * in the state stop_after = 1 leaves (pccb200_gof_dims returns the GOF-wide canvas); continue with pccb200_gof_resume. */
+int  pccb200_gof_pack_ra( pccb200_gof* gof, int total_frames, const int* patch_counts, const pccb200_patch* patches, const uint8_t* occ,
+                          const size_t* occ_sizes, const int* local_frame );
 /* Lossy geometry codec: run pccb200_encode_gof / pccb200_gof_resume with stop_after = 2, hand GOF_OM_VIDEO / GOF_GEO0 / GOF_GEO1 to
  * the codec, give the DECODED luma planes back (any pointer may be NULL = keep the source), then pccb200_gof_resume(gof, W, H, 0)
  * reconstructs from them exactly as PCCEncoder::encode does after videoEncoder.compress replaced `video` by the reconstruction

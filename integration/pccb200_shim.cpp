@@ -212,6 +212,12 @@ int stageB1( Session& s, const PCCEncoderParameters& params, PCCContext& context
     for ( size_t i = 0; i < R; ++i ) p2p[i] = PCCVector3<size_t>( b32[3 * i], b32[3 * i + 1], b32[3 * i + 2] );
     partitions[f].resize( R );
     if ( R ) pccb200_gof_get( s.gof, int( f ), PCCB200_GOF_REC_PARTITION, partitions[f].data() );
+    // what generatePointCloud also leaves behind (PCCCodec.cpp:683, 843, 888-950): the patch of every point in the cloud itself and the
+    // point counts of the tile, which colorPointCloud (:1348) and the conformance log (PCCEncoder.cpp:605) read
+    for ( size_t i = 0; i < R; ++i ) reconstructs[f].setPointPatchIndex( i, 0, partitions[f][i] );
+    tile.setTotalNumberOfRegularPoints( R );
+    tile.setTotalNumberOfEOMPoints( 0 );
+    tile.setTotalNumberOfRawPoints( 0 );
     // generatePointCloud leaves the block-precision occupancy in the tile (PCCCodec.cpp:559-572)
     auto&       occ = tile.getOccupancyMap();
     const auto& om  = context.getVideoOccupancyMap().getFrame( f ).getChannel( 0 );
@@ -276,6 +282,7 @@ int decodeFrame( Session& s, PCCContext& context, size_t frameIdx, size_t occupa
                                      xyz.data(), p2p.data(), partition.data(), bnd.data(), &R );
   if ( rc != PCCB200_OK ) return rc;
   reconstruct.clear();
+  reconstruct.addColors();  // (generatePointCloud: PCCCodec.cpp:539)
   reconstruct.resize( R );
   auto& pointToPixel = tile.getPointToPixel();
   pointToPixel.resize( R );
@@ -284,6 +291,10 @@ int decodeFrame( Session& s, PCCContext& context, size_t frameIdx, size_t occupa
     reconstruct.setBoundaryPointType( i, bnd[i] );
     pointToPixel[i] = PCCVector3<size_t>( p2p[3 * i], p2p[3 * i + 1], p2p[3 * i + 2] );
   }
+  for ( size_t i = 0; i < R; ++i ) reconstruct.setPointPatchIndex( i, 0, partition[i] );
+  tile.setTotalNumberOfRegularPoints( R );  // (PCCCodec.cpp:843, 888-950: read by colorPointCloud and the conformance log)
+  tile.setTotalNumberOfEOMPoints( 0 );
+  tile.setTotalNumberOfRawPoints( 0 );
   auto& map = tile.getOccupancyMap();  // block-precision occupancy, as generatePointCloud leaves it (PCCCodec.cpp:559-572)
   map.assign( W * H, 0 );
   for ( size_t y = 0; y < H; ++y )

@@ -237,10 +237,39 @@ void installPacking( FrameState& fs, int occRes ) {
 }
 
 // a15: random-access packing of the whole GOF (constrainedPack + global patch allocation): every frame is placed against the
-// previous one, so this runs once per GOF after all frames are segmented - metadata on the host, placement searches on the device
-void packGofRa( pccb200_gof* g, int minW, int minH ) {
-  const int               occRes = g->prm.occupancy_resolution;
-  std::vector<ra::Frame>  frames( g->nframes );
+// previous one, so this runs once per GOF after all frames are segmented - metadata on the host, placement searches on the device.
+// `all` = the patch records + block occupancies of ALL frames of the GOF in frame order; localOf[f] = index of frame f among the
+// frames this GOF object holds, or -1 (sharded GOF: the frame lives on another rank). The packing is deterministic, so every rank
+// that runs it on the same records gets the same result and installs the placements of its own frames.
+void packRaAndInstall( pccb200_gof* g, std::vector<ra::Frame>& all, const std::vector<int>& localOf, int minW, int minH ) {
+  const int occRes = g->prm.occupancy_resolution;
+  if ( !packGofRandomAccess( all, occRes, size_t( minW ), size_t( minH ), g->ctx->raPack, &g->ctx->prof, g->ctx->stream ) )
+    throw std::runtime_error( "random-access packing exceeded the packer's canvas limits" );
+  for ( size_t f = 0; f < all.size(); ++f ) {
+    if ( localOf[f] < 0 ) continue;
+    FrameState& fs = *g->frames[localOf[f]];
+    fs.packed.clear();
+    std::vector<uint8_t> arena;
+    for ( auto& p : all[f].patches ) {
+      p.m.occ_offset = int64_t( arena.size() );
+      arena.insert( arena.end(), p.occ.begin(), p.occ.end() );
+      fs.packed.push_back( p.m );
+    }
+    fs.seg.occ.reserve( arena.size() + 1 );
+    fs.seg.occElems = arena.size();
+    if ( !arena.empty() ) {
+      PCC_CUDA( cudaMemcpyAsync( fs.seg.occ, arena.data(), arena.size(), cudaMemcpyHostToDevice, fs.stream ) );
+      streamWait( fs.stream );
+    }
+    fs.heightPx = int( all[f].height );
+    fs.widthPx  = int( all[f].width );
+    installPacking( fs, occRes );
+  }
+}
+
+// the gof's own frames as packer input (patch records in creation order + their block occupancies from the device arena)
+std::vector<ra::Frame> ownRaFrames( pccb200_gof* g ) {
+  std::vector<ra::Frame> frames( g->nframes );
   for ( int f = 0; f < g->nframes; ++f ) {
     FrameState&          fs = *g->frames[f];
     std::vector<uint8_t> occ( fs.seg.occElems );
@@ -256,28 +285,24 @@ void packGofRa( pccb200_gof* g, int minW, int minH ) {
       p.occ.assign( occ.begin() + p.m.occ_offset, occ.begin() + p.m.occ_offset + size_t( p.m.size_u0 ) * p.m.size_v0 );
     }
   }
-  if ( !packGofRandomAccess( frames, occRes, size_t( minW ), size_t( minH ), g->ctx->raPack, &g->ctx->prof, g->ctx->stream ) )
-    throw std::runtime_error( "random-access packing exceeded the packer's canvas limits" );
-  for ( int f = 0; f < g->nframes; ++f ) {
-    FrameState& fs = *g->frames[f];
-    fs.packed.clear();
-    std::vector<uint8_t> arena;
-    for ( auto& p : frames[f].patches ) {
-      p.m.occ_offset = int64_t( arena.size() );
-      arena.insert( arena.end(), p.occ.begin(), p.occ.end() );
-      fs.packed.push_back( p.m );
-    }
-    fs.seg.occ.reserve( arena.size() + 1 );
-    fs.seg.occElems = arena.size();
-    if ( !arena.empty() ) {
-      PCC_CUDA( cudaMemcpyAsync( fs.seg.occ, arena.data(), arena.size(), cudaMemcpyHostToDevice, fs.stream ) );
-      streamWait( fs.stream );
-    }
-    fs.heightPx = int( frames[f].height );
-    fs.widthPx  = int( frames[f].width );
-    installPacking( fs, occRes );
-  }
+  return frames;
 }
+
+void packGofRa( pccb200_gof* g, int minW, int minH ) {
+  std::vector<ra::Frame> frames = ownRaFrames( g );
+  std::vector<int>       localOf( g->nframes );
+  for ( int f = 0; f < g->nframes; ++f ) localOf[f] = f;
+  packRaAndInstall( g, frames, localOf, minW, minH );
+}
+
+// a14: one canvas size per GOF (PCCEncoder::resizeTileGeometryVideo + resizeGeometryVideo, PCCEncoder.cpp:5546-5634)
+void setGofCanvas( pccb200_gof* g, size_t W, size_t H ) {
+  g->W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), g->H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
+}
+
+// host copies of the patch lists (KBs of metadata + the per-patch maps downstream reference code reads). packedOrder: the records of
+// fs.packed with the maps re-laid out in that order; otherwise (a GOF stopped after the segmentation) the records in creation order.
+int hostPatchLists( pccb200_gof* g, bool packedOrder );
 
 size_t copyOut( void* dst, const void* dev, size_t elems, size_t elemBytes, cudaStream_t s ) {
   if ( dst && elems ) {
@@ -353,9 +378,95 @@ void collectProfiles( pccb200_gof* g ) {
   }
 }
 
+int hostPatchLists( pccb200_gof* g, bool packedOrder ) {
+  g->lists.assign( g->nframes, pccb200_patchlist() );
+  return forEachFrame( g, [&]( FrameState& fs, int f ) {
+    pccb200_patchlist& pl = g->lists[f];
+    pl.patches            = packedOrder ? fs.packed : fs.seg.patches;
+    std::vector<int16_t> depth( fs.seg.depthElems );
+    std::vector<uint8_t> occ( fs.seg.occElems );
+    {
+      ProfScope t( &fs.prof, "d2h_patches", fs.stream );
+      if ( fs.seg.depthElems ) PCC_CUDA( cudaMemcpyAsync( depth.data(), fs.seg.depth, fs.seg.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, fs.stream ) );
+      if ( fs.seg.occElems ) PCC_CUDA( cudaMemcpyAsync( occ.data(), fs.seg.occ, fs.seg.occElems, cudaMemcpyDeviceToHost, fs.stream ) );
+      streamWait( fs.stream );
+    }
+    // the device arenas are in creation order; hand the maps out in the order of the patch records
+    pl.depth.resize( fs.seg.depthElems ), pl.occ.resize( fs.seg.occElems );
+    size_t dOff = 0, oOff = 0;
+    for ( auto& m : pl.patches ) {
+      const size_t px = 2 * size_t( m.size_u ) * m.size_v, nb = size_t( m.size_u0 ) * m.size_v0;
+      std::copy( depth.begin() + m.depth_offset, depth.begin() + m.depth_offset + px, pl.depth.begin() + dOff );
+      std::copy( occ.begin() + m.occ_offset, occ.begin() + m.occ_offset + nb, pl.occ.begin() + oOff );
+      m.depth_offset = int64_t( dOff ), m.occ_offset = int64_t( oOff );
+      dOff += px, oOff += nb;
+    }
+  } );
+}
+
 }  // namespace
 
 extern "C" {
+
+// Sharded random access: the frames of a GOF live on several ranks, but every frame is packed against the previous
+// one (PCCEncoder.cpp:4778-4805) and the global patch allocation iterates over the whole GOF (:6838-6970). Each rank segments its
+// frames (pccb200_encode_gof with stop_after = 5), the ranks all-gather the patch records + block occupancies (KBs per frame:
+// pccb200_gof_patches / pccb200_patches_get with a NULL depth pointer), and every rank calls this with the records of ALL frames
+// in frame order: the packing is deterministic, so all ranks compute the same placements; each installs those of its own frames.
+//   patch_counts[f]            patches of frame f (f = 0 .. total_frames-1)
+//   patches                    the records of all frames, concatenated; occ_offset relative to the frame's own occupancy block
+//   occ, occ_sizes[f]          the frames' block occupancies, concatenated / bytes per frame
+//   local_frame[f]             index of frame f among the frames of `gof`, or -1 if another rank holds it
+// Afterwards the GOF is in the state pccb200_encode_gof( stop_after = 1 ) leaves (pccb200_gof_dims = the GOF-wide canvas).
+int pccb200_gof_pack_ra( pccb200_gof* g, int totalFrames, const int* patchCounts, const pccb200_patch* patches, const uint8_t* occ,
+                         const size_t* occSizes, const int* localFrame ) {
+  if ( !g || totalFrames < g->nframes || !patchCounts || !occSizes || !localFrame ) return PCCB200_ERR_BAD_ARG;
+  if ( g->stage != 0 || g->prm.global_patch_allocation == 0 ) return PCCB200_ERR_STATE;
+  return guarded( g->ctx, [&]() -> int {
+    std::vector<ra::Frame> all( totalFrames );
+    std::vector<int>       localOf( totalFrames, -1 ), seen( g->nframes, 0 );
+    size_t                 pAt = 0, oAt = 0;
+    for ( int f = 0; f < totalFrames; ++f ) {
+      if ( patchCounts[f] < 0 || ( patchCounts[f] && ( !patches || !occ ) ) ) return PCCB200_ERR_BAD_ARG;
+      if ( localFrame[f] >= g->nframes ) return PCCB200_ERR_BAD_ARG;
+      if ( localFrame[f] >= 0 ) {
+        if ( seen[localFrame[f]]++ || size_t( patchCounts[f] ) != g->frames[localFrame[f]]->seg.patches.size() ) return PCCB200_ERR_BAD_ARG;
+        localOf[f] = localFrame[f];
+      }
+      all[f].patches.resize( patchCounts[f] );
+      for ( int i = 0; i < patchCounts[f]; ++i ) {
+        ra::Patch& p = all[f].patches[i];
+        p.m          = patches[pAt + i];
+        const size_t nb = size_t( p.m.size_u0 ) * p.m.size_v0;
+        if ( p.m.size_u0 < 0 || p.m.size_v0 < 0 || p.m.occ_offset < 0 || size_t( p.m.occ_offset ) + nb > occSizes[f] ) return PCCB200_ERR_BAD_ARG;
+        p.occ.assign( occ + oAt + p.m.occ_offset, occ + oAt + p.m.occ_offset + nb );
+        p.m.best_match_idx = -1, p.m.is_global = 0;
+        if ( localOf[f] >= 0 ) {  // the device arenas of a local frame are addressed by ITS records (the exchanged copies are re-based)
+          const pccb200_patch& own = g->frames[localOf[f]]->seg.patches[i];
+          if ( own.index != p.m.index || own.size_u != p.m.size_u || own.size_v != p.m.size_v ) return PCCB200_ERR_BAD_ARG;
+          p.m.depth_offset = own.depth_offset;
+        }
+      }
+      pAt += size_t( patchCounts[f] ), oAt += occSizes[f];
+    }
+    for ( int f = 0; f < g->nframes; ++f )
+      if ( !seen[f] ) return PCCB200_ERR_BAD_ARG;
+    const int minW = g->prm.geometry_bitdepth_3d > 11 ? 2560 : 1280, minH = 1280;
+    try {
+      packRaAndInstall( g, all, localOf, minW, minH );
+    } catch ( const std::exception& e ) {
+      g->ctx->lastError = e.what();
+      return PCCB200_ERR_CUDA;
+    }
+    size_t W = minW, H = minH;
+    for ( auto& fr : all ) H = std::max( H, fr.height ), W = std::max( W, fr.width );  // (all frames are here: the GOF-wide maximum)
+    setGofCanvas( g, W, H );
+    g->stage = 1;
+    const int rc = hostPatchLists( g, true );
+    collectProfiles( g );
+    return rc;
+  } );
+}
 
 int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz, const uint8_t* const* rgb, const size_t* n,
                         const pccb200_seg_params* prm, int occupancyPrecision, int stopAfter, pccb200_gof** out ) {
@@ -363,6 +474,7 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
   if ( !segParamsSupported( *prm ) || prm->occupancy_resolution != 16 || occupancyPrecision < 1 || 16 % occupancyPrecision != 0 ||
        prm->map_count_minus1 != 1 || ( prm->global_patch_allocation != 0 && prm->global_patch_allocation != 1 ) )
     return PCCB200_ERR_UNSUPPORTED;
+  if ( stopAfter < 0 || stopAfter == 4 || stopAfter > 5 || ( stopAfter == 5 && prm->global_patch_allocation == 0 ) ) return PCCB200_ERR_BAD_ARG;
   *out = nullptr;
   return guarded( ctx, [&]() -> int {
     pccb200_gof* g = new pccb200_gof();
@@ -403,9 +515,9 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
         segmentFrameAfterWalk( fs, g->prm );
         streamWait( fs.stream );
       }
-      if ( g->prm.global_patch_allocation == 0 ) packFrame( fs, g->prm, minW, minH, 2, 1.0 );
+      if ( g->prm.global_patch_allocation == 0 && stopAfter != 5 ) packFrame( fs, g->prm, minW, minH, 2, 1.0 );
     } );
-    if ( rc == PCCB200_OK && g->prm.global_patch_allocation != 0 ) {
+    if ( rc == PCCB200_OK && g->prm.global_patch_allocation != 0 && stopAfter != 5 ) {
       try {
         packGofRa( g, minW, minH );
       } catch ( const std::exception& e ) {
@@ -423,42 +535,23 @@ int pccb200_encode_gof( pccb200_ctx* ctx, int nframes, const int16_t* const* xyz
       delete g;
       return rc;
     }
-    // a14: one canvas size per GOF (PCCEncoder::resizeTileGeometryVideo + resizeGeometryVideo, PCCEncoder.cpp:5546-5634)
-    size_t W = minW, H = minH;
-    for ( auto* fs : g->frames ) H = std::max( H, size_t( fs->heightPx ) ), W = std::max( W, size_t( fs->widthPx ) );
-    g->W = size_t( std::ceil( double( W ) / 64.0 ) * 64 ), g->H = size_t( std::ceil( double( H ) / 64.0 ) * 64 );
-    g->stage = 1;
-    if ( stopAfter != 1 ) {
-      rc = runCanvasStages( g, stopAfter );
-      if ( rc != PCCB200_OK ) {
-        delete g;
-        return rc;
+    if ( stopAfter == 5 ) {  // sharded random access: the packing needs the other ranks' patch records first (pccb200_gof_pack_ra)
+      g->stage = 0;
+      rc       = hostPatchLists( g, false );
+    } else {
+      size_t W = minW, H = minH;
+      for ( auto* fs : g->frames ) H = std::max( H, size_t( fs->heightPx ) ), W = std::max( W, size_t( fs->widthPx ) );
+      setGofCanvas( g, W, H );
+      g->stage = 1;
+      if ( stopAfter != 1 ) {
+        rc = runCanvasStages( g, stopAfter );
+        if ( rc != PCCB200_OK ) {
+          delete g;
+          return rc;
+        }
       }
+      rc = hostPatchLists( g, true );
     }
-    // host copies of the packed patch lists (KBs of metadata + the per-patch maps downstream reference code reads)
-    g->lists.resize( nframes );
-    rc = forEachFrame( g, [&]( FrameState& fs, int f ) {
-      pccb200_patchlist& pl = g->lists[f];
-      pl.patches            = fs.packed;
-      std::vector<int16_t> depth( fs.seg.depthElems );
-      std::vector<uint8_t> occ( fs.seg.occElems );
-      {
-        ProfScope t( &fs.prof, "d2h_patches", fs.stream );
-        if ( fs.seg.depthElems ) PCC_CUDA( cudaMemcpyAsync( depth.data(), fs.seg.depth, fs.seg.depthElems * sizeof( int16_t ), cudaMemcpyDeviceToHost, fs.stream ) );
-        if ( fs.seg.occElems ) PCC_CUDA( cudaMemcpyAsync( occ.data(), fs.seg.occ, fs.seg.occElems, cudaMemcpyDeviceToHost, fs.stream ) );
-        streamWait( fs.stream );
-      }
-      // the device arenas are in creation order; hand the maps out in packed order (the order of the patch records)
-      pl.depth.resize( fs.seg.depthElems ), pl.occ.resize( fs.seg.occElems );
-      size_t dOff = 0, oOff = 0;
-      for ( auto& m : pl.patches ) {
-        const size_t px = 2 * size_t( m.size_u ) * m.size_v, nb = size_t( m.size_u0 ) * m.size_v0;
-        std::copy( depth.begin() + m.depth_offset, depth.begin() + m.depth_offset + px, pl.depth.begin() + dOff );
-        std::copy( occ.begin() + m.occ_offset, occ.begin() + m.occ_offset + nb, pl.occ.begin() + oOff );
-        m.depth_offset = int64_t( dOff ), m.occ_offset = int64_t( oOff );
-        dOff += px, oOff += nb;
-      }
-    } );
     collectProfiles( g );
     if ( rc != PCCB200_OK ) {
       delete g;

@@ -665,7 +665,7 @@ Product.encode_gof = _product_encode_gof
 class ProductGof:
     """staged use of the GOF entry points (pack -> [all-reduce canvas] -> resume -> fetch hand-off products)"""
 
-    def __init__(self, product, frames, params, occupancy_precision=4):
+    def __init__(self, product, frames, params, occupancy_precision=4, stop_after=1):
         self.p, L = product, product.lib
         _product_encode_gof.__doc__  # (signatures are declared there)
         L.pccb200_encode_gof.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_i16p), C.POINTER(c_u8p), C.POINTER(C.c_size_t), C.POINTER(SegParams),
@@ -677,7 +677,7 @@ class ProductGof:
         L.pccb200_gof_resume.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
         self.n, self._xs, self._cs, xp, cp, ns = _frames_args(frames)
         self.h = C.c_void_p()
-        product._check(L.pccb200_encode_gof(product.ctx, self.n, xp, cp, ns, C.byref(params), occupancy_precision, 1, C.byref(self.h)))
+        product._check(L.pccb200_encode_gof(product.ctx, self.n, xp, cp, ns, C.byref(params), occupancy_precision, stop_after, C.byref(self.h)))
 
     def dims(self, f=0):
         w, hh, r = C.c_size_t(), C.c_size_t(), C.c_size_t()
@@ -702,6 +702,41 @@ class ProductGof:
         if self.h:
             self.p.lib.pccb200_gof_free(self.h)
             self.h = C.c_void_p()
+
+    def patch_records(self, f):
+        """(patch records, block occupancies) of local frame f - what a sharded random-access GOF exchanges (no depth maps)"""
+        L = self.p.lib
+        L.pccb200_gof_patches.restype = C.c_void_p
+        L.pccb200_gof_patches.argtypes = [C.c_void_p, C.c_int]
+        pl = L.pccb200_gof_patches(self.h, f)
+        patches = np.zeros(L.pccb200_patches_count(pl), dtype=PATCH_DTYPE)
+        occ = np.zeros(L.pccb200_patches_occ_elems(pl), np.uint8)
+        self.p._check(L.pccb200_patches_get(pl, patches.ctypes.data_as(C.c_void_p), None, ptr(occ, c_u8p)))
+        return patches, occ
+
+    def patch_list(self, f):
+        """PatchSet of local frame f (records, depth maps, occupancies) as pccb200_gof_patches hands it out"""
+        L = self.p.lib
+        L.pccb200_gof_patches.restype = C.c_void_p
+        L.pccb200_gof_patches.argtypes = [C.c_void_p, C.c_int]
+        pl = L.pccb200_gof_patches(self.h, f)
+        patches = np.zeros(L.pccb200_patches_count(pl), dtype=PATCH_DTYPE)
+        depth = np.zeros(L.pccb200_patches_depth_elems(pl), np.int16)
+        occ = np.zeros(L.pccb200_patches_occ_elems(pl), np.uint8)
+        self.p._check(L.pccb200_patches_get(pl, patches.ctypes.data_as(C.c_void_p), ptr(depth, c_i16p), ptr(occ, c_u8p)))
+        return PatchSet(patches, depth, occ)
+
+    def pack_ra(self, records, local_of):
+        """records: [(patch records, occupancies)] of ALL frames of the GOF in frame order; local_of[f]: local index of frame f or -1"""
+        L = self.p.lib
+        L.pccb200_gof_pack_ra.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, c_u8p, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        total = len(records)
+        counts = (C.c_int * total)(*[len(r[0]) for r in records])
+        sizes = (C.c_size_t * total)(*[len(r[1]) for r in records])
+        local = (C.c_int * total)(*[int(x) for x in local_of])
+        patches = np.concatenate([np.ascontiguousarray(r[0], PATCH_DTYPE) for r in records]) if total else np.zeros(0, PATCH_DTYPE)
+        occ = np.concatenate([np.ascontiguousarray(r[1], np.uint8) for r in records] + [np.zeros(1, np.uint8)])
+        self.p._check(L.pccb200_gof_pack_ra(self.h, total, counts, patches.ctypes.data_as(C.c_void_p), ptr(occ, c_u8p), sizes, local))
 
 
 def _product_generate_point_cloud(self, patches, occ_video, geo0, geo1, width, height, occupancy_precision=4):

@@ -65,8 +65,11 @@ def encoder_command(binary, work, out, condition, frames, iterations):
         for k in ("geometryConfig", "attributeConfig", "occupancyMapConfig", "geometryMPConfig"):
             f.write("%s: %s\n" % (k, dummy))
     os.makedirs(out, exist_ok=True)
+    # A non-empty colour-space configuration with an empty colorSpaceConversionPath selects the reference's INTERNAL converter
+    # (PCCVideoEncoder.cpp:318-334: "RGB444ToYUV420_8_4" / "YUV420ToYUV444_8_0"); the files only have to exist
+    # (PCCEncoderParameters.cpp:832-846). With empty names the attribute frames would reach the codec without any conversion.
     return [os.path.join(BIN, binary), "--config=" + cfg, "--uncompressedDataPath=" + os.path.join(work, "frame_%04d.ply"), "--startFrameNumber=0",
-            "--frameCount=%d" % frames, "--nbThread=1", "--colorSpaceConversionConfig=", "--inverseColorSpaceConversionConfig=",
+            "--frameCount=%d" % frames, "--nbThread=1", "--colorSpaceConversionConfig=" + dummy, "--inverseColorSpaceConversionConfig=" + dummy,
             "--iterationCountRefineSegmentation=%d" % iterations, "--keepIntermediateFiles=1",
             "--compressedStreamPath=" + os.path.join(out, "s.bin"), "--reconstructedDataPath=" + os.path.join(out, "rec_%04d.ply")] + \
            ["--videoEncoder%sPath=%s" % (k, STUB) for k in ("Occupancy", "Geometry", "Attribute")] + \
@@ -129,3 +132,36 @@ def test_b200_encoder_application_writes_the_reference_files(condition, frames, 
     assert "s.bin" in want and any("_log.txt" in n for n in want) and sum(n.endswith(".yuv") for n in want) >= 6
     bad = [n for n in want if want[n] != got[n]]
     assert bad == [], "files differ between the reference application and its B200 build: %s" % bad
+
+
+def decoder_command(binary, work, stream, out):
+    dummy = os.path.join(work, "codec.cfg")
+    os.makedirs(out, exist_ok=True)
+    return [os.path.join(BIN, binary), "--compressedStreamPath=" + stream, "--inverseColorSpaceConversionConfig=" + dummy, "--colorTransform=0",
+            "--nbThread=1", "--startFrameNumber=0", "--reconstructedDataPath=" + os.path.join(out, "dec_%04d.ply"), "--computeChecksum=1"] + \
+           ["--videoDecoder%sPath=%s" % (k, STUB) for k in ("Occupancy", "Geometry", "Attribute")]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_apps(), reason="oracle/_ref/bin not built (needs /root/reference at build time)")
+def test_b200_decoder_application_reconstructs_what_the_reference_decoder_does(tmp_path):
+    """PccAppDecoder with PCCCodec::generatePointCloud on the B200 (PCCDecoder.cpp:349-351 -> pccb200shim::decodeFrame): the stream of
+    the unmodified encoder decodes to the same clouds as with the unmodified decoder, and the decoder's own checksum test against the
+    encoder's reconstruction (--computeChecksum) passes for both"""
+    work = str(tmp_path)
+    make_inputs(work, 2, 0.2)
+    assert run(encoder_command("PccAppEncoder", work, os.path.join(work, "enc"), "ai_r3", 2, 6), os.path.join(work, "enc.log")) == 0
+    stream = os.path.join(work, "enc", "s.bin")
+    outs = {}
+    for binary in ("PccAppDecoder", "PccAppDecoder_b200"):
+        out = os.path.join(work, binary)
+        rc = run(decoder_command(binary, work, stream, out), os.path.join(work, binary + ".log"))
+        if rc != 0:
+            with open(os.path.join(work, binary + ".log")) as f:
+                sys.stderr.write(f.read()[-3000:])
+        assert rc == 0, binary
+        outs[binary] = {n: h for n, h in digest_dir(out).items() if n.endswith(".ply")}
+        assert len(outs[binary]) == 2
+    assert outs["PccAppDecoder"] == outs["PccAppDecoder_b200"]
+    enc = digest_dir(os.path.join(work, "enc"))
+    assert [outs["PccAppDecoder"]["dec_%04d.ply" % f] for f in range(2)] == [enc["rec_%04d.ply" % f] for f in range(2)], "decoder output != encoder reconstruction"

@@ -126,3 +126,47 @@ def test_canvas_exchange_protocol(tmp_path, oracle):
             for i, f in enumerate(range(rank, len(frames), world)):
                 for k, v in whole[f].data.items():
                     assert np.array_equal(got["f%d_%d" % (i, k)], v), "GOF %d frame %d product %s" % (g, f, bindings.GOF_NAMES[k])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# random access: the one exchange of a sharded GOF (mpeg-pcc-tmc2_b200/sharding.py gather_patch_records) - every rank must end up with
+# the records of all frames, identical to what a single process sees; feeding them to the packer then gives the unsharded packing
+# (the product's pccb200_gof_pack_ra needs a GPU: tests/test_ra_pack.py; here the oracle's packer is the stand-in)
+def _gather_worker(rank, world, port, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "mpeg-pcc-tmc2_b200"))
+    import bindings
+    from sharding import gather_patch_records
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = bindings.Oracle()
+    frames = _frames() + [(np.zeros((0, 3), np.int16), np.zeros((0, 3), np.uint8))]      # incl. an empty frame
+    prm = bindings.ctc_seg_params(bits=10, iterations=4, weight=(1.0, 1.0, 1.0))
+    local = []
+    for f in range(rank, len(frames), world):
+        seg = orc.segment_frame_patches(frames[f][0], frames[f][1], prm) if len(frames[f][0]) else None
+        patches = seg.patches if seg is not None else np.zeros(0, bindings.PATCH_DTYPE)
+        occ = seg.occ if seg is not None else np.zeros(0, np.uint8)
+        local.append((f, patches, occ))
+    got = gather_patch_records(dist, local, len(frames), bindings.PATCH_DTYPE)
+    np.savez(os.path.join(out_dir, "g_rank%d.npz" % rank), **{"p%d" % f: got[f][0] for f in range(len(frames))},
+             **{"o%d" % f: got[f][1] for f in range(len(frames))})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_patch_records(tmp_path, oracle):
+    import bindings
+    world, port = 2, 29531 + (os.getpid() % 200)
+    mp.spawn(_gather_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    frames = _frames() + [(np.zeros((0, 3), np.int16), np.zeros((0, 3), np.uint8))]
+    prm = bindings.ctc_seg_params(bits=10, iterations=4, weight=(1.0, 1.0, 1.0))
+    ranks = [np.load(tmp_path / ("g_rank%d.npz" % r)) for r in range(world)]
+    for f in range(len(frames)):
+        if len(frames[f][0]):
+            seg = oracle.segment_frame_patches(frames[f][0], frames[f][1], prm)
+            want_p, want_o = seg.patches, seg.occ
+        else:
+            want_p, want_o = np.zeros(0, bindings.PATCH_DTYPE), np.zeros(0, np.uint8)
+        for r in range(world):
+            assert np.array_equal(ranks[r]["p%d" % f], want_p) and np.array_equal(ranks[r]["o%d" % f], want_o), "frame %d on rank %d" % (f, r)

@@ -137,3 +137,39 @@ def test_gpu_ra_gof_vs_reference_fixture(product):
     for f, (a, b) in enumerate(zip(got, gold)):
         for k in b:
             assert a[k] == b[k], "random-access frame %d product %s differs from the reference fixture" % (f, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shards", [2, 3])
+def test_gpu_sharded_random_access_gof_equals_unsharded(shards, product):
+    """SURVEY 8e, random access: the frames of a GOF held by several ranks (here: several library contexts on one GPU), segmentation
+    per shard (stop_after = 5), ONE exchange of patch records + block occupancies, the deterministic packing replicated on every
+    shard (pccb200_gof_pack_ra), image formation per shard - every product must equal the unsharded GOF's"""
+    frames = [synth.figure(scale=0.14, seed=4, frame=f) for f in range(5)] + [synth.sphere(radius=22, center=70, seed=2)]
+    prm = bindings.ctc_seg_params(bits=10, iterations=4, weight=product.weight_normal(frames[0][0], 11))
+    prm.global_patch_allocation = 1
+    whole = product.encode_gof(frames, prm, occupancy_precision=2)
+    ctxs = [bindings.Product(0) for _ in range(shards)]
+    owner = [f % shards for f in range(len(frames))]                       # frame f -> shard f mod shards
+    local = [[f for f in range(len(frames)) if owner[f] == r] for r in range(shards)]
+    gofs = [bindings.ProductGof(ctxs[r], [frames[f] for f in local[r]], prm, 2, stop_after=5) for r in range(shards)]
+    records = [None] * len(frames)                                         # the all-gather: every shard learns every frame's records
+    for r in range(shards):
+        for i, f in enumerate(local[r]):
+            records[f] = gofs[r].patch_records(i)
+    for r in range(shards):
+        gofs[r].pack_ra(records, [local[r].index(f) if owner[f] == r else -1 for f in range(len(frames))])
+    dims = {gofs[r].dims(0)[:2] for r in range(shards)}
+    assert dims == {(whole[0].width, whole[0].height)}, "every shard must arrive at the GOF-wide canvas"
+    for r in range(shards):
+        W, H, _ = gofs[r].dims(0)
+        gofs[r].resume(W, H, 0)
+        for i, f in enumerate(local[r]):
+            got = gofs[r].patch_list(i)
+            for fld in got.patches.dtype.names:
+                assert np.array_equal(got.patches[fld], whole[f].patches.patches[fld]), "frame %d patch field %s" % (f, fld)
+            assert np.array_equal(got.depth, whole[f].patches.depth) and np.array_equal(got.occ, whole[f].patches.occ)
+            for what, name in bindings.GOF_NAMES.items():
+                assert np.array_equal(gofs[r].fetch(i, what), whole[f].data[what]), "frame %d %s (shard %d)" % (f, name, r)
+        gofs[r].free()
+        ctxs[r].close()

@@ -1,9 +1,7 @@
 #!/bin/bash
-# One gpurun call (1 GPU): GPU test-suite, smoke, default bench + single-GOF latency, ncu launch list of one frame and full captures
-# of the kernels changed this round.
+# One gpurun call (1 GPU): GPU test-suite (incl. the application-level drop-in), default bench + single-GOF latency, launch list.
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q --durations=5 ) > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
-( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+( timeout 1200 python -m pytest tests -m gpu -q --durations=5 ) > gpurun_out/pytest_gpu.log 2>&1; tail -15 gpurun_out/pytest_gpu.log
 summ() { python - "$1" <<'P'
 import json,sys
 try:
@@ -16,6 +14,3 @@ timeout 300 python bench.py --steps 4 --warmup 1 --gofs-in-flight 1 --no-cpu-bas
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches_traffic.csv \
   python bench.py --frames 1 --steps 1 --warmup 0 --gofs-in-flight 1 --no-cpu-baseline > gpurun_out/ncu_list.out 2> gpurun_out/ncu_list.err
 echo "ncu list rc=$?"; wc -l gpurun_out/launches_traffic.csv
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:kSweep|kLocalSubtrees|kScanSweep1|kApply2Assign|kPushPullTail' -c 10 -o gpurun_out/prof_r02 -f \
-  python bench.py --frames 1 --steps 1 --warmup 0 --gofs-in-flight 1 --no-cpu-baseline > gpurun_out/ncu_full.out 2> gpurun_out/ncu_full.err
-echo "ncu full rc=$?"; ls -la gpurun_out/prof_r02.ncu-rep

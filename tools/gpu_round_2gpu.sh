@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 summ() { python - "$1" <<'P'
 import json,sys
 try:
-    d=json.load(open('gpurun_out/bench_%s.json'%sys.argv[1])); print(sys.argv[1], round(d['value'],2), round(d['e2e']['value'],2), d['host_ms_per_gof'], d.get('canvas_exchange'))
+    d=json.load(open('gpurun_out/bench_%s.json'%sys.argv[1])); print(sys.argv[1], round(d['value'],2), round(d['e2e']['value'],2), d['host_ms_per_gof'], d.get('exchange'))
 except Exception as e: print(sys.argv[1],'ERR', e)
 P
 }
