@@ -184,20 +184,14 @@ __device__ __forceinline__ unsigned long long globalTimerNs() {
   return t;
 }
 
-// `stageRows`: the rows of ALL neighbours of the point being expanded are requested (asynchronous copies into shared memory) as
-// soon as its own row has arrived, i.e. one memory round trip before the walk knows which of them - if any - it visits next. When
-// the next point is one of the neighbours just improved (about half of the steps), its row is then already on chip and the step
-// costs one dependent round trip (best[] of its neighbours) instead of two.
-constexpr int kWalkSmemWords = 224 + 2 * 16 * 32;  // fixed part of the walk's shared memory (words) before the bit-tree levels
-__global__ void __launch_bounds__( 32, 1 ) kWalk( const WalkArgs* __restrict__ batch, unsigned long long* __restrict__ stamps, int stageRows ) {
+__global__ void __launch_bounds__( 32, 1 ) kWalk( const WalkArgs* __restrict__ batch, unsigned long long* __restrict__ stamps, int earlyPrefetch ) {
   const WalkArgs a = batch[blockIdx.x];
   if ( threadIdx.x == 0 ) stamps[2 * blockIdx.x] = globalTimerNs();
   extern __shared__ __align__( 16 ) uint32_t smemAll[];
   uint2* const    rowBuf = reinterpret_cast<uint2*>( smemAll );  // 16 x 8 bytes: landing zone of the next point's neighbour row
   uint64_t* const pendBuf = reinterpret_cast<uint64_t*>( smemAll + 32 );  // 32 x 16 bytes: re-read leaf words (one pair per lane)
   uint32_t* const stage  = smemAll + 160;                        // 2 x 32 words: hand-over of new entries to free hot slots
-  uint2* const    cand   = reinterpret_cast<uint2*>( smemAll + 224 );  // 2 x 16 rows of 16 x 8 bytes: the neighbours' rows (ping-pong)
-  uint32_t* const smem32 = smemAll + kWalkSmemWords;             // upper levels of the bit-tree
+  uint32_t* const smem32 = smemAll + 224;                        // upper levels of the bit-tree
   Levels          lv{ smem32, smem32 + a.nL1, smem32 + a.nL1 + a.nL2, smem32 + a.nL1 + a.nL2 + a.nL3 };
   const int                  lane = threadIdx.x;
   const unsigned             FULL = 0xffffffffu;
@@ -287,19 +281,14 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( const WalkArgs* __restrict__ b
     // (the row travels global -> shared by an asynchronous copy: a register load would be waited for at the first copy of its
     // destination register, which the compiler places right behind the load)
     if ( lane < 16 ) cpAsync8( rowBuf + lane, a.rows + size_t( cur ) * 16 + lane );
-    const uint2* rowAt = rowBuf;  // where the row of the point being expanded lands: rowBuf, or a staged neighbour row
-    int          pp    = 0;       // staging buffer the NEXT step's candidates go to
     for ( ;; ) {
       cpAsyncWait();
       __syncwarp();
-      const uint2 slot = lane < 16 ? rowAt[lane] : make_uint2( kInvalid, 0 );
+      const uint2 slot = lane < 16 ? rowBuf[lane] : make_uint2( kInvalid, 0 );
       __syncwarp();
-      if ( stageRows && lane < 16 && slot.x != kInvalid ) {  // 8 x 16 bytes per neighbour row, straight from L2
-        const uint4* src4 = reinterpret_cast<const uint4*>( a.rows + size_t( slot.x ) * 16 );
-        uint4*       dst4 = reinterpret_cast<uint4*>( cand + ( pp * 16 + lane ) * 16 );
-#pragma unroll
-        for ( int q = 0; q < 8; ++q ) cpAsync16( dst4 + q, src4 + q );
-      }
+      // the rows of ALL neighbours are pulled into L2 now, one round trip before the walk knows (from best[]) which of them it may
+      // visit next: when the next point is one of them (about half of the steps) its row fetch then hits L2 instead of DRAM
+      if ( earlyPrefetch && lane < 16 && slot.x != kInvalid ) prefetchL2( a.rows + size_t( slot.x ) * 16 );
       if ( pendWord != kNone ) cpAsync16( pendBuf + 2 * lane, a.L0 + ( pendWord & ~1u ) );
       cpAsyncCommit();
       // ---- A: state of the neighbours and of the hot entries' ends (best[] is private to this warp: L1-cached loads)
@@ -344,19 +333,13 @@ __global__ void __launch_bounds__( 32, 1 ) kWalk( const WalkArgs* __restrict__ b
       const bool toQueue = improved && !( newWins && lane == src );
       if ( toQueue ) {
         a.best[slot.x] = r;
-        prefetchL2( a.rows + size_t( slot.x ) * 16 );  // the row the visit of slot.x will read
+        if ( !earlyPrefetch ) prefetchL2( a.rows + size_t( slot.x ) * 16 );  // the row the visit of slot.x will read
       }
       if ( newWins ? lane == src : lane == 0 ) {
         a.flip[next] = nextFlip ? 1 : 0;
         a.best[next] = kVisited;
       }
-      if ( stageRows && newWins ) {
-        rowAt = cand + ( pp * 16 + src ) * 16;  // already on its way since the top of this step
-      } else {
-        rowAt = rowBuf;
-        if ( lane < 16 ) cpAsync8( rowBuf + lane, a.rows + size_t( next ) * 16 + lane );
-      }
-      pp ^= 1;
+      if ( lane < 16 ) cpAsync8( rowBuf + lane, a.rows + size_t( next ) * 16 + lane );
       cpAsyncCommit();
       // ---- D: queue upkeep. Leaf words drained in the previous step are unhooked before anything is inserted
       cpAsyncWaitAllButLatest();
@@ -556,7 +539,7 @@ void orientPrepare( OrientScratch& sc, OrientTemp& tmp, const short4* pts, const
   kFillU32<<<divUp( n, 256 ), 256, 0, s>>>( sc.best, n, kNone );
   PCC_LAUNCH_CHECK();
   a.L0 = sc.L0, a.best = sc.best, a.flip = sc.flip;
-  const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 + a.nL4 + kWalkSmemWords ) * 4;
+  const size_t smemBytes = size_t( a.nL1 + a.nL2 + a.nL3 + a.nL4 + 224 ) * 4;
   if ( smemBytes > 200 * 1024 ) throw CudaError{ cudaErrorInvalidValue, __FILE__, __LINE__ };
   memcpy( sc.walkArgs, &a, sizeof( a ) );
   sc.walkSmem = smemBytes;
@@ -589,11 +572,11 @@ void orientWalkBatch( OrientScratch* const* frames, int count, DevBuf<unsigned c
   devArgs.reserve( argBytes + args.size() * 16 );
   unsigned long long* stamps = reinterpret_cast<unsigned long long*>( devArgs.p + argBytes );
   PCC_CUDA( cudaMemcpyAsync( devArgs.p, args.data(), args.size() * sizeof( WalkArgs ), cudaMemcpyHostToDevice, s ) );
-  static const int stageRows = [] {  // (A/B switch of the neighbour-row staging; on by default)
-    const char* e = getenv( "PCCB200_WALK_STAGE_ROWS" );
+  static const int earlyPrefetch = [] {  // (A/B switch: prefetch the neighbours' rows before / after best[] is known)
+    const char* e = getenv( "PCCB200_WALK_EARLY_PREFETCH" );
     return e && e[0] == '0' ? 0 : 1;
   }();
-  kWalk<<<unsigned( args.size() ), 32, smem, s>>>( reinterpret_cast<const WalkArgs*>( devArgs.p ), stamps, stageRows );
+  kWalk<<<unsigned( args.size() ), 32, smem, s>>>( reinterpret_cast<const WalkArgs*>( devArgs.p ), stamps, earlyPrefetch );
   PCC_LAUNCH_CHECK();
   // The walks run for a second or more on one warp each. NOTHING is enqueued behind them - an event record or a dependent
   // kernel would sit at the head of the stream's hardware queue until they finish and hold up every other stream that shares

@@ -362,35 +362,12 @@ __device__ __forceinline__ void sweepVoxel( const SweepData& d, uint32_t v, int 
 
 // Sweep, launch 1 of 3: the voxels that are edge voxels at sweep start (the list kRecountAndActivate left, complete before this
 // launch) are dealt out by warp index - no tickets, no polling. Also clears the OTHER initial list's counter (the next sweep's).
-// A warp that has finished its share then helps with the tail: it takes tail entries that ALREADY exist (compare-and-swap on the
-// ticket counter, so no ticket is ever drawn for an entry that may never come) and leaves as soon as there is none - it never
-// waits for other CTAs. Whatever is appended after that is kSweepTail's.
 __device__ __forceinline__ unsigned ldVolatile( const unsigned* p ) { return *reinterpret_cast<const volatile unsigned*>( p ); }
 __global__ void __launch_bounds__( 128 ) kSweepStatic( SweepData d, const uint32_t* __restrict__ list, const unsigned* __restrict__ ctl, unsigned* __restrict__ nextCtl ) {
   const int      lane  = threadIdx.x & 31;
   const unsigned count = ctl[0], nWarps = gridDim.x * ( blockDim.x / 32 );
   if ( blockIdx.x == 0 && threadIdx.x == 0 ) nextCtl[0] = 0;
   for ( unsigned w = ( blockIdx.x * blockDim.x + threadIdx.x ) / 32; w < count; w += nWarps ) sweepVoxel( d, list[w], lane );
-  unsigned* tctl = d.tailCtl;
-  for ( ;; ) {
-    uint32_t v = kNoEntry;
-    if ( lane == 0 ) {
-      for ( ;; ) {
-        const unsigned t = ldVolatile( &tctl[1] );
-        if ( t >= ldVolatile( &tctl[0] ) ) break;
-        if ( atomicCAS( &tctl[1], t, t + 1 ) == t ) {
-          while ( ( v = ldVolatile( &d.tail[t] ) ) == kNoEntry ) __nanosleep( 20 );  // (reserved by a running warp: written at once)
-          break;
-        }
-      }
-    }
-    v = __shfl_sync( 0xffffffffu, v, 0 );
-    if ( v == kNoEntry ) return;
-    sweepVoxel( d, v, lane );
-    __threadfence();
-    __syncwarp();
-    if ( lane == 0 ) atomicAdd( &tctl[2], 1u );
-  }
 }
 
 // Sweep, launch 2 of 3: the voxels activated during the sweep - a persistent kernel over the growing tail list. A warp takes a
@@ -553,8 +530,12 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
     const char* e = getenv( "PCCB200_SWEEP_CTAS_PER_SM" );
     return e && atoi( e ) > 0 ? atoi( e ) : 8;
   }();
+  static const int tailCtasPerSm = [] {  // (the tail of a sweep is about as long as its initial list: same order of warps)
+    const char* e = getenv( "PCCB200_SWEEP_TAIL_CTAS_PER_SM" );
+    return e && atoi( e ) > 0 ? atoi( e ) : 4;
+  }();
   const int staticCtas = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * ctasPerSm ) );
-  const int tailCtas   = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * 4 ) );
+  const int tailCtas   = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * tailCtasPerSm ) );
   static const unsigned maxSleepNs = [] {
     const char* e = getenv( "PCCB200_SWEEP_MAX_SLEEP_NS" );
     return unsigned( e && atoi( e ) > 0 ? atoi( e ) : 2048 );

@@ -76,9 +76,12 @@ def encoder_command(binary, work, out, condition, frames, iterations):
            ["--videoEncoder%sCodecId=HMAPP" % k for k in ("Occupancy", "Geometry", "Attribute")]
 
 
-def run(cmd, log):
+def run(cmd, log, timeout=300):
     with open(log, "w") as f:
-        return subprocess.run(cmd, stdout=f, stderr=subprocess.STDOUT, cwd=os.path.dirname(log)).returncode
+        try:
+            return subprocess.run(cmd, stdout=f, stderr=subprocess.STDOUT, cwd=os.path.dirname(log), timeout=timeout).returncode
+        except subprocess.TimeoutExpired:
+            return -999
 
 
 def digest_dir(path):
