@@ -90,9 +90,11 @@ __device__ __forceinline__ void slotCut( const SlotView& sv, int s, bool rootLev
   decideCut( lo, hi, mn, mx, feat, cut );
 }
 
-__global__ void kInit( uint32_t* vind, int* slotOf, int n, SlotView sv, int* cnt ) {
+// ptsT is kept in tree order THROUGHOUT the build (ptsT[p] == pts[vind[p]]): every swap moves the point along with its index, so
+// the per-level passes read coordinates coalesced instead of gathering pts[vind[p]].
+__global__ void kInit( uint32_t* vind, int* slotOf, int n, SlotView sv, int* cnt, const short4* __restrict__ pts, short4* __restrict__ ptsT ) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ( i < n ) vind[i] = i, slotOf[i] = 0;
+  if ( i < n ) vind[i] = i, slotOf[i] = 0, ptsT[i] = pts[i];
   if ( i == 0 ) {
     sv.at( F_NODE, 0 ) = 0, sv.at( F_LO, 0 ) = 0, sv.at( F_HI, 0 ) = n;
     for ( int d = 0; d < 3; ++d ) sv.at( F_MM + d, 0 ) = INT_MAX, sv.at( F_MM + 3 + d, 0 ) = INT_MIN;
@@ -135,8 +137,7 @@ __global__ void kRootBox( SlotView sv, int* cnt, int* localRec, int4* nodes, int
 // ---- TOP phase, launch 1 of 5: scan of the sweep-1 flags (v < cut over [lo, hi)); the decision is stored for the later launches
 struct Sweep1Flags {
   SlotView        sv;
-  const short4*   pts;
-  const uint32_t* vind;
+  const short4*   ptsT;
   const int*      slotOf;
   bool            rootLevel;
   int             lastS, feat, cut;
@@ -148,14 +149,14 @@ struct Sweep1Flags {
       lastS = s;
     }
     if ( int( p ) == sv.at( F_LO, s ) ) sv.at( F_FEAT, s ) = feat, sv.at( F_CUT, s ) = cut;
-    return coord( pts[vind[p]], feat ) < cut ? 1u : 0u;
+    return coord( ptsT[p], feat ) < cut ? 1u : 0u;
   }
 };
 __global__ void __launch_bounds__( kScanThreads )
-    kScanSweep1( SlotView sv, const short4* __restrict__ pts, const uint32_t* __restrict__ vind, const int* __restrict__ slotOf, int n, int level,
+    kScanSweep1( SlotView sv, const short4* __restrict__ ptsT, const int* __restrict__ slotOf, int n, int level,
                  const int* __restrict__ cnt, uint32_t* __restrict__ S, unsigned long long* __restrict__ ctl ) {
   if ( cnt[C_LEVEL + level] == 0 ) return;
-  Sweep1Flags f{ sv, pts, vind, slotOf, level == 0, -1, 0, 0 };
+  Sweep1Flags f{ sv, ptsT, slotOf, level == 0, -1, 0, 0 };
   scanLookbackTile( f, S, size_t( n ), ctl );
 }
 
@@ -232,24 +233,28 @@ __global__ void kCompact( SlotView sv, SlotView nx, const uint32_t* __restrict__
 }
 
 // the swap of one sweep at position p: the i-th left-misplaced and the i-th (from the right) right-misplaced trade places
-__device__ __forceinline__ void applySwap( uint32_t* __restrict__ vind, const uint32_t* __restrict__ S, const uint32_t* __restrict__ tmpA,
-                                           const uint32_t* __restrict__ tmpB, int p, int subLo, int hi, uint32_t& cntOut ) {
+__device__ __forceinline__ void applySwap( uint32_t* __restrict__ vind, const short4* __restrict__ pts, short4* __restrict__ ptsT,
+                                           const uint32_t* __restrict__ S, const uint32_t* __restrict__ tmpA, const uint32_t* __restrict__ tmpB, int p,
+                                           int subLo, int hi, uint32_t& cntOut ) {
   const uint32_t cnt = S[hi] - S[subLo];
   cntOut             = cnt;
   if ( p < subLo ) return;
   const uint32_t i = p - subLo;
   const uint32_t f = S[p + 1] - S[p];
+  uint32_t id = 0xFFFFFFFFu;
   if ( i < cnt && !f ) {
-    vind[p] = tmpB[subLo + ( i - ( S[p] - S[subLo] ) )];
+    id = tmpB[subLo + ( i - ( S[p] - S[subLo] ) )];
   } else if ( i >= cnt && f ) {
-    vind[p] = tmpA[subLo + ( S[hi] - S[p + 1] )];
+    id = tmpA[subLo + ( S[hi] - S[p + 1] )];
   }
+  if ( id != 0xFFFFFFFFu ) vind[p] = id, ptsT[p] = pts[id];
 }
 
 // ---- launch 3: sweep-1 swap fused into the scan of the sweep-2 flags (v <= cut over [lo + lim1, hi))
 struct Sweep2Flags {
   SlotView        sv;
   const short4*   pts;
+  short4*         ptsT;
   uint32_t*       vind;
   const int*      slotOf;
   const uint32_t *S1, *tmpA, *tmpB;
@@ -258,24 +263,24 @@ struct Sweep2Flags {
     if ( s < 0 ) return 0u;
     const int lo = sv.at( F_LO, s ), hi = sv.at( F_HI, s );
     uint32_t  lim1;
-    applySwap( vind, S1, tmpA, tmpB, int( p ), lo, hi, lim1 );
+    applySwap( vind, pts, ptsT, S1, tmpA, tmpB, int( p ), lo, hi, lim1 );
     if ( int( p ) == lo ) sv.at( F_LIM1, s ) = int( lim1 );
     if ( int( p ) < lo + int( lim1 ) ) return 0u;
-    return coord( pts[vind[p]], sv.at( F_FEAT, s ) ) <= sv.at( F_CUT, s ) ? 1u : 0u;
+    return coord( ptsT[p], sv.at( F_FEAT, s ) ) <= sv.at( F_CUT, s ) ? 1u : 0u;
   }
 };
 __global__ void __launch_bounds__( kScanThreads )
-    kScanSweep2( SlotView sv, const short4* __restrict__ pts, uint32_t* __restrict__ vind, const int* __restrict__ slotOf, int n, int level,
+    kScanSweep2( SlotView sv, const short4* __restrict__ pts, short4* __restrict__ ptsT, uint32_t* __restrict__ vind, const int* __restrict__ slotOf, int n, int level,
                  const int* __restrict__ cnt, const uint32_t* __restrict__ S1, const uint32_t* __restrict__ tmpA, const uint32_t* __restrict__ tmpB,
                  uint32_t* __restrict__ S2, unsigned long long* __restrict__ ctl ) {
   if ( cnt[C_LEVEL + level] == 0 ) return;
-  Sweep2Flags f{ sv, pts, vind, slotOf, S1, tmpA, tmpB };
+  Sweep2Flags f{ sv, pts, ptsT, vind, slotOf, S1, tmpA, tmpB };
   scanLookbackTile( f, S2, size_t( n ), ctl );
 }
 
 // ---- launch 5: sweep-2 swap, tight split bounds (divlow = max of the left child along feat, divhigh = min of the right child,
 // straight into the node record), the slot of every position for the next level and that level's min/max
-__global__ void kApply2Assign( SlotView sv, SlotView nx, const short4* __restrict__ pts, uint32_t* __restrict__ vind, int* __restrict__ slotOf,
+__global__ void kApply2Assign( SlotView sv, SlotView nx, const short4* __restrict__ pts, short4* __restrict__ ptsT, uint32_t* __restrict__ vind, int* __restrict__ slotOf,
                                const uint32_t* __restrict__ S2, const uint32_t* __restrict__ tmpA, const uint32_t* __restrict__ tmpB, int n, int level,
                                const int* __restrict__ cnt, int4* __restrict__ nodes ) {
   if ( cnt[C_LEVEL + level] == 0 ) return;
@@ -285,10 +290,10 @@ __global__ void kApply2Assign( SlotView sv, SlotView nx, const short4* __restric
   if ( s < 0 ) return;
   const int lo = sv.at( F_LO, s ), hi = sv.at( F_HI, s );
   uint32_t  unused;
-  applySwap( vind, S2, tmpA, tmpB, p, lo + sv.at( F_LIM1, s ), hi, unused );
+  applySwap( vind, pts, ptsT, S2, tmpA, tmpB, p, lo + sv.at( F_LIM1, s ), hi, unused );
   const int    idx  = sv.at( F_IDX, s );
   const int    side = ( p - lo ) < idx ? 0 : 1;
-  const short4 q    = pts[vind[p]];
+  const short4 q    = ptsT[p];
   const int    v    = coord( q, sv.at( F_FEAT, s ) );
   const int    child = sv.at( F_CHILD0 + side, s );
   slotOf[p]         = child;
@@ -437,8 +442,7 @@ __global__ void __launch_bounds__( kLocalThreads )
     const int* r   = localRec + size_t( rec ) * kLocalRecInts;
     const int  glo = r[1], m = r[2] - r[1];
     for ( int i = threadIdx.x; i < m; i += kLocalThreads ) {
-      const uint32_t id = vind[glo + i];
-      sm.sid[i] = id, sm.sp[i] = pts[id];
+      sm.sid[i] = vind[glo + i], sm.sp[i] = ptsT[glo + i];
       sm.nodeOf[i] = 0;
     }
     int nCur = 0, depth = r[9], which = 0;
@@ -706,7 +710,7 @@ void kdBuild( KdTree& t, const short4* xyz4, size_t n, cudaStream_t s ) {
   unsigned long long* const ctl = reinterpret_cast<unsigned long long*>( ( reinterpret_cast<uintptr_t>( t.scanTmp.p ) + 7 ) & ~uintptr_t( 7 ) );
   const int mode = N <= kLeafMaxSize ? 2 : ( N <= kLocalMax ? 1 : 0 );  // root: leaf / one local subtree / top phase
 
-  kInit<<<gridN, TB, 0, s>>>( t.vind, t.slotOf, N, SlotView{ t.slotI[0], maxSlots }, cnt );
+  kInit<<<gridN, TB, 0, s>>>( t.vind, t.slotOf, N, SlotView{ t.slotI[0], maxSlots }, cnt, t.pts, t.ptsT );
   kRootMinMax<<<gridN, TB, 0, s>>>( SlotView{ t.slotI[0], maxSlots }, t.pts, N );
   kRootBox<<<1, 1, 0, s>>>( SlotView{ t.slotI[0], maxSlots }, cnt, localRec, t.nodes, N, mode );
   PCC_LAUNCH_CHECK();
@@ -715,11 +719,11 @@ void kdBuild( KdTree& t, const short4* xyz4, size_t n, cudaStream_t s ) {
     SlotView sv{ t.slotI[level & 1], maxSlots }, nx{ t.slotI[( level + 1 ) & 1], maxSlots };
     unsigned long long* c1 = ctl + size_t( 2 * level ) * ctlWords;
     unsigned long long* c2 = c1 + ctlWords;
-    kScanSweep1<<<gridScan, kScanThreads, 0, s>>>( sv, t.pts, t.vind, t.slotOf, N, level, cnt, S1, c1 );
+    kScanSweep1<<<gridScan, kScanThreads, 0, s>>>( sv, t.ptsT, t.slotOf, N, level, cnt, S1, c1 );
     kCompact<1><<<gridN, TB, 0, s>>>( sv, nx, t.vind, t.slotOf, S1, t.tmpA, t.tmpB, N, level, cnt, t.nodes, localRec, int( maxLocal ) );
-    kScanSweep2<<<gridScan, kScanThreads, 0, s>>>( sv, t.pts, t.vind, t.slotOf, N, level, cnt, S1, t.tmpA, t.tmpB, S2, c2 );
+    kScanSweep2<<<gridScan, kScanThreads, 0, s>>>( sv, t.pts, t.ptsT, t.vind, t.slotOf, N, level, cnt, S1, t.tmpA, t.tmpB, S2, c2 );
     kCompact<2><<<gridN, TB, 0, s>>>( sv, nx, t.vind, t.slotOf, S2, t.tmpA, t.tmpB, N, level, cnt, t.nodes, localRec, int( maxLocal ) );
-    kApply2Assign<<<gridN, TB, 0, s>>>( sv, nx, t.pts, t.vind, t.slotOf, S2, t.tmpA, t.tmpB, N, level, cnt, t.nodes );
+    kApply2Assign<<<gridN, TB, 0, s>>>( sv, nx, t.pts, t.ptsT, t.vind, t.slotOf, S2, t.tmpA, t.tmpB, N, level, cnt, t.nodes );
     PCC_LAUNCH_CHECK();
   };
   auto launchLocal = [&]() {
