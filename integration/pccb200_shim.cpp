@@ -302,4 +302,35 @@ int decodeFrame( Session& s, PCCContext& context, size_t frameIdx, size_t occupa
   return PCCB200_OK;
 }
 
+namespace {
+int needCtx( Session& s ) { return s.ctx ? PCCB200_OK : pccb200_create( 0, &s.ctx ); }
+}  // namespace
+
+int smoothGeometry( Session& s, PCCPointSet3& reconstruct, const std::vector<uint32_t>& partition, size_t gridSize, double threshold ) {
+  int rc = needCtx( s );
+  if ( rc != PCCB200_OK ) return rc;
+  const size_t n = reconstruct.getPointCount();
+  if ( n == 0 ) return PCCB200_OK;
+  // positions_ is vector<PCCVector3<int16_t>>, boundaryPointTypes_ vector<uint16_t>: the arrays the ABI takes, updated in place
+  return pccb200_smooth_geometry( s.ctx, &reconstruct.getPositions()[0][0], reconstruct.getBoundaryPointTypes().data(), partition.data(), n,
+                                  int( gridSize ), threshold );
+}
+
+int transferColors16( Session& s, PCCPointSet3& source, PCCPointSet3& target ) {
+  int rc = needCtx( s );
+  if ( rc != PCCB200_OK ) return rc;
+  if ( source.getPointCount() == 0 || target.getPointCount() == 0 ) return PCCB200_OK;
+  return pccb200_transfer_colors16_smoothed( s.ctx, &source.getPositions()[0][0], &source.getColors16bit()[0][0], source.getPointCount(),
+                                             &target.getPositions()[0][0], &target.getColors16bit()[0][0], target.getBoundaryPointTypes().data(),
+                                             target.getPointCount() );
+}
+
+int yuv16ToRgb8( Session& s, PCCPointSet3& cloud ) {
+  int rc = needCtx( s );
+  if ( rc != PCCB200_OK ) return rc;
+  const size_t n = cloud.getPointCount();
+  if ( n == 0 ) return PCCB200_OK;
+  return pccb200_yuv16_to_rgb8( s.ctx, &cloud.getColors16bit()[0][0], n, &cloud.getColors()[0][0] );
+}
+
 }  // namespace pccb200shim

@@ -46,4 +46,15 @@ int stageB2( Session& s, pcc::PCCContext& context );
 int decodeFrame( Session& s, pcc::PCCContext& context, size_t frameIdx, size_t occupancyPrecision, pcc::PCCPointSet3& reconstruct,
                  std::vector<uint32_t>& partition );
 
+// Post-reconstruction chain as PCCEncoder::encode (PccLibEncoder/source/PCCEncoder.cpp:647-702) and
+// PCCDecoder::decode (PccLibDecoder/source/PCCDecoder.cpp:401-470) run it under the CTC - drop-in bodies for three calls:
+//   smoothGeometry   : smoothPointCloudPostprocess( reconstruct, colorTransform, ppSEIParams, partition ) with gridSmoothing
+//                      (positions and boundary point types of `reconstruct` are updated in place)
+//   transferColors16 : tempFrameBuffer.transferColors16bitBP( reconstruct, filterType 1, 0, false, 8, 1, true, true, true, false, 4, 4,
+//                      1000, 1000, 1000 * 256, 1000 * 256 ) - new 16-bit colours for the points the smoothing moved
+//   yuv16ToRgb8      : reconstruct.convertYUV16ToRGB8()
+int smoothGeometry( Session& s, pcc::PCCPointSet3& reconstruct, const std::vector<uint32_t>& partition, size_t gridSize, double threshold );
+int transferColors16( Session& s, pcc::PCCPointSet3& source, pcc::PCCPointSet3& target );
+int yuv16ToRgb8( Session& s, pcc::PCCPointSet3& cloud );
+
 }  // namespace pccb200shim

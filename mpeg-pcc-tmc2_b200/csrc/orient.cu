@@ -572,9 +572,12 @@ void orientWalkBatch( OrientScratch* const* frames, int count, DevBuf<unsigned c
   devArgs.reserve( argBytes + args.size() * 16 );
   unsigned long long* stamps = reinterpret_cast<unsigned long long*>( devArgs.p + argBytes );
   PCC_CUDA( cudaMemcpyAsync( devArgs.p, args.data(), args.size() * sizeof( WalkArgs ), cudaMemcpyHostToDevice, s ) );
-  static const int earlyPrefetch = [] {  // (A/B switch: prefetch the neighbours' rows before / after best[] is known)
+  // (A/B switch: prefetch the neighbours' rows to L2 before best[] is known instead of after, for the improved ones only. Measured on
+  //  the B200, profiles/r02f_*: 1231 vs 1210 ms per 0.83 Mpts walk alone, 52.8 vs 51.4 Mpts/s with 8 GOFs in flight - within the
+  //  run-to-run noise, so the variant with less traffic stays the default)
+  static const int earlyPrefetch = [] {
     const char* e = getenv( "PCCB200_WALK_EARLY_PREFETCH" );
-    return e && e[0] == '0' ? 0 : 1;
+    return e && e[0] == '1' ? 1 : 0;
   }();
   kWalk<<<unsigned( args.size() ), 32, smem, s>>>( reinterpret_cast<const WalkArgs*>( devArgs.p ), stamps, earlyPrefetch );
   PCC_LAUNCH_CHECK();

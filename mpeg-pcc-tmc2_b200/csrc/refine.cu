@@ -281,37 +281,6 @@ __global__ void kRecountAndActivate( VoxState st, const uint32_t* __restrict__ v
   if ( on ) list[base + __popc( m & ( ( 1u << ( threadIdx.x & 31 ) ) - 1 ) )] = v;
 }
 
-// relabel the points of one processed voxel (one warp per voxel, one lane per point); s = its smoothed histogram
-__device__ __forceinline__ void relabelVoxel( VoxState st, uint32_t v, int lane, const uint32_t s[6], const double* __restrict__ weight,
-                                              const uint32_t* __restrict__ voxStart, const uint32_t* __restrict__ voxCount,
-                                              const uint32_t* __restrict__ idsSorted, const double* __restrict__ normals, uint8_t* __restrict__ partition ) {
-  uint8_t edgeHere = st.edge[v];
-  if ( edgeHere == NO_EDGE ) edgeHere = INDIRECT_EDGE;  // activated during this sweep
-  if ( edgeHere != M_DIRECT_EDGE ) {
-    int used = 0;
-#pragma unroll
-    for ( int k = 0; k < 6; ++k ) used += s[k] != 0;
-    if ( used == 1 && s[st.ppi[v]] > 0 ) return;
-  }
-  const double   wv = weight[v];
-  const uint32_t st0 = voxStart[v], c = voxCount[v];
-  for ( uint32_t j = lane; j < c; j += 32 ) {
-    const uint32_t p = idsSorted[st0 + j];
-    const double   x = normals[3 * size_t( p )], y = normals[3 * size_t( p ) + 1], z = normals[3 * size_t( p ) + 2];
-    const double   d[6] = {x * 1.0 + y * 0.0 + z * 0.0,  x * 0.0 + y * 1.0 + z * 0.0,  x * 0.0 + y * 0.0 + z * 1.0,
-                           x * -1.0 + y * 0.0 + z * 0.0, x * 0.0 + y * -1.0 + z * 0.0, x * 0.0 + y * 0.0 + z * -1.0};
-    int            best = 0;
-    double         bs   = d[0] + wv * double( uint16_t( s[0] ) );
-#pragma unroll
-    for ( int k = 1; k < 6; ++k ) {
-      const double sc = d[k] + wv * double( uint16_t( s[k] ) );
-      if ( sc > bs ) bs = sc, best = k;
-    }
-    partition[p] = uint8_t( best );
-  }
-  if ( lane == 0 ) st.dirty[v] = 1;
-}
-
 // One voxel of a sweep (one warp): smooth = sum of the neighbours' histograms (uint16 wrap-around like ScoresVector_t), top = first
 // arg-max; the 2nd voxel classification: NO_EDGE neighbours whose PPI differs are marked, and those with a larger index join this
 // very sweep (appended to the TAIL list); then the voxel's points are relabelled (argmax of n.o_k + w_v * smooth_k) - scores,
@@ -328,36 +297,79 @@ struct SweepData {
   uint32_t*       tail;     // voxels activated during the sweep
   unsigned*       tailCtl;  // [0] entries reserved, [1] next ticket, [2] entries finished
 };
+// Loads are issued in three dependency levels, everything that only needs v first (the structure's pointers may alias as far as
+// the compiler knows, so program order is what lets the loads of the later steps overlap the adjacency gather):
+//   1. adjOff/adjLen, nearLen/nearData, edge/ppi/weight/voxStart/voxCount of v      2. adjData, edge/ppi of the near voxels, point ids
+//   3. the neighbours' score rows, the points' normals
 __device__ __forceinline__ void sweepVoxel( const SweepData& d, uint32_t v, int lane ) {
   const uint32_t off = d.adjOff[v], len = d.adjLen[v];
+  const int      nl  = d.nearLen[v];
+  const uint32_t o   = lane < kMaxNear ? d.nearData[size_t( v ) * kMaxNear + lane] : 0u;
+  uint8_t        edgeHere = d.st.edge[v];
+  const uint8_t  ppiHere  = d.st.ppi[v];
+  const double   wv  = d.weight[v];
+  const uint32_t st0 = d.voxStart[v], c = d.voxCount[v];
+  uint8_t        edgeNear = 0xff, ppiNear = 0;
+  if ( lane < nl ) edgeNear = d.st.edge[o], ppiNear = d.st.ppi[o];
+  // (a voxel holds at most 64 points: 4 x 4 x 4 positions -> two per lane)
+  const bool     has0 = uint32_t( lane ) < c, has1 = uint32_t( lane ) + 32 < c;
+  const uint32_t p0 = has0 ? d.idsSorted[st0 + lane] : 0u, p1 = has1 ? d.idsSorted[st0 + lane + 32] : 0u;
   uint32_t       s[6] = {0, 0, 0, 0, 0, 0};
   for ( uint32_t i = lane; i < len; i += 32 ) {
     const uint4 r = *reinterpret_cast<const uint4*>( d.st.score + size_t( d.adjData[off + i] ) * 8 );
     s[0] += r.x & 0xffff, s[1] += r.x >> 16, s[2] += r.y & 0xffff, s[3] += r.y >> 16, s[4] += r.z & 0xffff, s[5] += r.z >> 16;
   }
+  double n0[3] = {0.0, 0.0, 0.0}, n1[3] = {0.0, 0.0, 0.0};
+  if ( has0 ) n0[0] = d.normals[3 * size_t( p0 )], n0[1] = d.normals[3 * size_t( p0 ) + 1], n0[2] = d.normals[3 * size_t( p0 ) + 2];
+  if ( has1 ) n1[0] = d.normals[3 * size_t( p1 )], n1[1] = d.normals[3 * size_t( p1 ) + 1], n1[2] = d.normals[3 * size_t( p1 ) + 2];
 #pragma unroll
   for ( int k = 0; k < 6; ++k ) s[k] = __reduce_add_sync( 0xffffffffu, s[k] ) & 0xffffu;
   int top = 0;
 #pragma unroll
   for ( int k = 1; k < 6; ++k )
     if ( s[k] > s[top] ) top = k;
-  if ( lane < d.nearLen[v] ) {
-    const uint32_t o = d.nearData[size_t( v ) * kMaxNear + lane];
-    if ( d.st.edge[o] == NO_EDGE && d.st.ppi[o] != top ) {
-      d.st.mark[o] = 1;
-      if ( o > v ) {
-        // byte-granular test-and-set on the active flags
-        unsigned*      word = reinterpret_cast<unsigned*>( d.st.active ) + ( o >> 2 );
-        const unsigned bit  = 1u << ( 8 * ( o & 3 ) );
-        const unsigned old  = atomicOr( word, bit );
-        if ( !( old & bit ) ) {
-          const unsigned at = atomicAdd( &d.tailCtl[0], 1u );
-          *reinterpret_cast<volatile uint32_t*>( &d.tail[at] ) = o;
-        }
+  if ( lane < nl && edgeNear == NO_EDGE && ppiNear != top ) {
+    d.st.mark[o] = 1;
+    if ( o > v ) {
+      // byte-granular test-and-set on the active flags
+      unsigned*      word = reinterpret_cast<unsigned*>( d.st.active ) + ( o >> 2 );
+      const unsigned bit  = 1u << ( 8 * ( o & 3 ) );
+      const unsigned old  = atomicOr( word, bit );
+      if ( !( old & bit ) ) {
+        const unsigned at = atomicAdd( &d.tailCtl[0], 1u );
+        *reinterpret_cast<volatile uint32_t*>( &d.tail[at] ) = o;
       }
     }
   }
-  relabelVoxel( d.st, v, lane, s, d.weight, d.voxStart, d.voxCount, d.idsSorted, d.normals, d.partition );
+  // relabel the voxel's points (one lane per point)
+  if ( edgeHere == NO_EDGE ) edgeHere = INDIRECT_EDGE;  // activated during this sweep
+  if ( edgeHere != M_DIRECT_EDGE ) {
+    int used = 0;
+#pragma unroll
+    for ( int k = 0; k < 6; ++k ) used += s[k] != 0;
+    if ( used == 1 && s[ppiHere] > 0 ) return;
+  }
+  auto label = [&]( const double n[3] ) {
+    const double x = n[0], y = n[1], z = n[2];
+    const double dd[6] = {x * 1.0 + y * 0.0 + z * 0.0,  x * 0.0 + y * 1.0 + z * 0.0,  x * 0.0 + y * 0.0 + z * 1.0,
+                          x * -1.0 + y * 0.0 + z * 0.0, x * 0.0 + y * -1.0 + z * 0.0, x * 0.0 + y * 0.0 + z * -1.0};
+    int          best = 0;
+    double       bs   = dd[0] + wv * double( uint16_t( s[0] ) );
+#pragma unroll
+    for ( int k = 1; k < 6; ++k ) {
+      const double sc = dd[k] + wv * double( uint16_t( s[k] ) );
+      if ( sc > bs ) bs = sc, best = k;
+    }
+    return uint8_t( best );
+  };
+  if ( has0 ) d.partition[p0] = label( n0 );
+  if ( has1 ) d.partition[p1] = label( n1 );
+  for ( uint32_t jj = lane + 64; jj < c; jj += 32 ) {  // (not reached with voxel dimension 4; kept for generality)
+    const uint32_t p  = d.idsSorted[st0 + jj];
+    const double   nn[3] = {d.normals[3 * size_t( p )], d.normals[3 * size_t( p ) + 1], d.normals[3 * size_t( p ) + 2]};
+    d.partition[p]       = label( nn );
+  }
+  if ( lane == 0 ) d.st.dirty[v] = 1;
 }
 
 // Sweep, launch 1 of 3: the voxels that are edge voxels at sweep start (the list kRecountAndActivate left, complete before this

@@ -9,9 +9,11 @@
                                                                                                     -> pccb200shim::stageA
                     the generatePointCloud loop (:319-334) + generateAttributeVideo (:341)           -> pccb200shim::stageB1
                     the attribute padding loop (:344-424)                                           -> pccb200shim::stageB2
-                  everything else (video compression calls, post-processing, bitstream) stays as it is.
+                    smoothPointCloudPostprocess (:650) and transferColors16bitBP (:657-672) of the post-processing loop
+                                                                       -> pccb200shim::smoothGeometry / transferColors16
+                  everything else (video compression calls incl. colour conversion, colorPointCloud, bitstream) stays as it is.
   PCCDecoder.cpp  PCCDecoder::decode (PccLibDecoder/source/PCCDecoder.cpp:349-351): the generatePointCloud call of the tile loop
-                  -> pccb200shim::decodeFrame
+                  -> pccb200shim::decodeFrame; the same two post-processing calls (:404, :416-432) as in the encoder
 
 Every edit is an exact-text replacement that must match exactly once inside the function it targets; the script fails loudly when
 the reference text differs (another TMC2 version). oracle/Makefile (targets `apps`, `apps_b200`) compiles the unmodified and the
@@ -41,6 +43,31 @@ def replace_once(body, old, new, what):
     if body.count(old) != 1:
         sys.exit("patch_reference: %s: expected exactly one match of %r, found %d" % (what, old[:60], body.count(old)))
     return body.replace(old, new)
+
+
+def patch_postprocessing(body, session, what):
+    """the post-reconstruction chain of the CTC path, the same three calls in encode() and decode()"""
+    body = replace_once(body, "        smoothPointCloudPostprocess( reconstruct, params_.colorTransform_, ppSEIParams, partition );\n", """        {  // grid-based geometry smoothing on the B200
+          const int b200rc = pccb200shim::smoothGeometry( %s, reconstruct, partition, ppSEIParams.gridSize_, ppSEIParams.thresholdSmoothing_ );
+          if ( b200rc != 0 ) {
+            fprintf( stderr, "pccb200: smoothGeometry failed with %%d\\n", b200rc );
+            exit( -1 );
+          }
+        }
+""" % session, what + ": smoothPointCloudPostprocess")
+    a = body.index("            tempFrameBuffer.transferColors16bitBP( reconstruct,")
+    b = body.index(";", body.index("// maxColorDist2Bwd", a)) + 1   # the end of that call statement
+    if body.count("            tempFrameBuffer.transferColors16bitBP( reconstruct,") != 1:
+        sys.exit("patch_reference: %s: transferColors16bitBP call not unique" % what)
+    body = body[:a] + """            if ( params_.attrTransferFilterType_ == 1 && !isAttributes444 ) {  // colour transfer onto the smoothed cloud on the B200
+              const int b200rc = pccb200shim::transferColors16( %s, tempFrameBuffer, reconstruct );
+              if ( b200rc != 0 ) {
+                fprintf( stderr, "pccb200: transferColors16 failed with %%d\\n", b200rc );
+                exit( -1 );
+              }
+            } else
+""" % session + body[a:b] + body[b:]
+    return body
 
 
 def patch_encoder(src):
@@ -82,6 +109,7 @@ def patch_encoder(src):
       }
     } else if ( params_.attributeBGFill_ < 3 ) {
 """, "attribute padding loop")
+    body = patch_postprocessing(body, "g_pccb200", "PCCEncoder::encode")
     head = src[:a]
     marker = '#include "PCCEncoder.h"\n'
     if head.count(marker) != 1:
@@ -104,6 +132,7 @@ def patch_decoder(src):
         }
       }
 """, "generatePointCloud")
+    body = patch_postprocessing(body, "g_pccb200dec", "PCCDecoder::decode")
     head = src[:a]
     marker = '#include "PCCDecoder.h"\n'
     if head.count(marker) != 1:
