@@ -428,7 +428,7 @@ __device__ __forceinline__ void localSwap( LocalSmem& sm, const LNode* cur, int 
 }
 
 __global__ void __launch_bounds__( kLocalThreads )
-    kLocalSubtrees( const short4* __restrict__ pts, uint32_t* __restrict__ vind, short4* __restrict__ ptsT, int4* __restrict__ nodes,
+    kLocalSubtrees( uint32_t* __restrict__ vind, short4* __restrict__ ptsT, int4* __restrict__ nodes,
                     const int* __restrict__ localRec, int* __restrict__ cnt, int maxLocal ) {
   extern __shared__ __align__( 16 ) unsigned char smemRaw[];
   LocalSmem& sm = *reinterpret_cast<LocalSmem*>( smemRaw );
@@ -728,7 +728,7 @@ void kdBuild( KdTree& t, const short4* xyz4, size_t n, cudaStream_t s ) {
   };
   auto launchLocal = [&]() {
     const int grid = std::max( 1, std::min( 148 * 2, divUp( n, 1024 ) ) );
-    kLocalSubtrees<<<grid, kLocalThreads, sizeof( LocalSmem ), s>>>( t.pts, t.vind, t.ptsT, t.nodes, localRec, cnt, int( maxLocal ) );
+    kLocalSubtrees<<<grid, kLocalThreads, sizeof( LocalSmem ), s>>>( t.vind, t.ptsT, t.nodes, localRec, cnt, int( maxLocal ) );
     PCC_LAUNCH_CHECK();
   };
   // read-back: the first 16 counters (nodes, local records, depth, ticket, overflow flag, top depth, ..., root box at 8) + slots left at `level`
