@@ -187,7 +187,7 @@ def config(args, npts, frames_per_rank, world):
             "frames_in_flight": frames_per_rank * lanes, "gofs_in_flight": lanes, "host_cores": host_cores(),
             "parallelism": ("frames of a GOF sharded over %d GPU(s), canvas size reduced by NCCL all-reduce(MAX), up to %d GOFs per collective, off the critical path"
                             % (world, args.exchange_batch)) if sharded else
-                           "frames of a GOF sharded over %d GPU(s) (frame f -> GPU f mod G), one NCCL all-gather of the patch records per GOF, packing replicated" % world,
+                           "frames of a GOF sharded over %d GPU(s) (frame f -> GPU f mod G), one all-gather of the patch records (host data, gloo) per GOF, packing replicated" % world,
             "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2",
             "host_buffers": "pinned (inputs and the frames handed to the video codec)",
             "handoff": "occupancy video + geometry D0/D1 luma + attribute T0/T1 converted to 8-bit YUV 4:2:0 on the device (the conversion the reference does inside compress())",
@@ -320,8 +320,15 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
-        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # the exchange gets its own communicator + high-priority stream
-        exchange_group = dist.new_group(backend="nccl", pg_options=opts)
+        if args.condition == "ai":   # the canvas exchange gets its own NCCL communicator + high-priority stream (hidden behind image formation)
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            exchange_group = dist.new_group(backend="nccl", pg_options=opts)
+        else:
+            # Random access: the lanes WAIT for the exchanged patch records (the packing needs them), and the records are KBs of HOST
+            # data (pccb200_gof_patches). Measured on 2 x B200 (profiles/r02j_bench_2gpu_ra_nccl.json): staged through the busy GPUs and
+            # NCCL, one all-gather took 1.2 s (the collective kernels and copies queue behind the frames' kernels) and the ranks spent
+            # 5.4 s per GOF waiting. Host data goes over a host transport: a gloo group beside the NCCL one.
+            exchange_group = dist.new_group(backend="gloo")
     sharded = world > 1
     sharded_ra = sharded and args.condition == "ra"
     sys.path.insert(0, os.path.join(ROOT, "mpeg-pcc-tmc2_b200"))
@@ -392,7 +399,7 @@ def main():
         lock = threading.Lock()
         state = {"next": 0}
         ex = CanvasExchange(dist, count, batch=args.exchange_batch, group=exchange_group, device=local) if sharded and not sharded_ra else None
-        rx = RecordExchange(dist, count, total_frames, bindings.PATCH_DTYPE, group=exchange_group, device=local) if sharded_ra else None
+        rx = RecordExchange(dist, count, total_frames, bindings.PATCH_DTYPE, group=exchange_group, device=None) if sharded_ra else None
 
         def worker(lane):
             torch.cuda.set_device(local)   # (the current device is per thread)
@@ -534,7 +541,7 @@ def main():
         "gpu_mem_used_gb": round((torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 2**30, 1),
     }
     if xstats is not None:
-        out["exchange"] = {"kind": "patch-record all-gather (2 collectives per GOF)" if sharded_ra else "canvas-size all-reduce(MAX)",
+        out["exchange"] = {"kind": "patch-record all-gather (host data over gloo, 2 collectives per GOF)" if sharded_ra else "canvas-size all-reduce(MAX) over NCCL",
                            "collectives": xstats[0], "ms_per_collective": round(xstats[1] / max(1, xstats[0]) * 1e3, 2), "gofs_reformed": stats["reformed"]}
     counts_path = os.path.join(ROOT, "profiles", "launch_counts.json")
     if os.path.exists(counts_path):
