@@ -348,7 +348,7 @@ def main():
     for p in prods:
         p.profile(True)
     total_pts = sum(len(f[0]) for f in frames)
-    outbuf, outlock = dict(), threading.Lock()   # ONE set of pinned hand-off buffers: the lanes take turns copying out (45 ms per GOF)
+    outbuf = dict()   # pinned hand-off buffers, one set per lane (no lock: the lanes' copies overlap instead of queueing behind each other)
 
     def phase_a(lane):
         """a1..a13 of one GOF: segmentation (incl. the orientation walk) + packing (sharded random access: segmentation only)"""
@@ -358,19 +358,19 @@ def main():
     total_frames = args.frames * world
     local_of = [(f // world if f % world == rank else -1) for f in range(total_frames)]
 
-    def phase_b(g, W, H):
+    def phase_b(lane, g, W, H):
         """a16..a26 + hand-off: images, reconstruction, colour, attribute images; D2H of every frame the codec would receive"""
         g.resume(W, H, 0)
         t1 = time.perf_counter()
         nbytes = 0
-        with outlock:
-            for f in range(len(frames)):
-                for what in HANDOFF:
-                    cnt = g.count(f, what)
-                    if (f, what) not in outbuf or outbuf[(f, what)].size != cnt:
-                        outbuf[(f, what)] = pinned((cnt,), bindings.GOF_DTYPES[what])
-                    g.fetch(f, what, outbuf[(f, what)])
-                    nbytes += outbuf[(f, what)].nbytes
+        for f in range(len(frames)):
+            for what in HANDOFF:
+                cnt = g.count(f, what)
+                key = (lane, f, what)
+                if key not in outbuf or outbuf[key].size != cnt:
+                    outbuf[key] = pinned((cnt,), bindings.GOF_DTYPES[what])
+                g.fetch(f, what, outbuf[key])
+                nbytes += outbuf[key].nbytes
         return t1, time.perf_counter(), nbytes
 
     gof_log = []       # per GOF: lane, absolute times of start / packed / resumed / fetched / verified / freed
@@ -424,20 +424,20 @@ def main():
                 W, H = gof.dims(0)[:2]
                 if ex is not None:
                     ex.post(g, W, H)
-                t1, t2, nbytes = phase_b(gof, W, H)
+                t1, t2, nbytes = phase_b(lane, gof, W, H)
                 tv = t2
                 if ex is not None:
                     Wg, Hg = ex.wait(g)
                     tv = time.perf_counter()
                     if (Wg, Hg) != (W, H):   # another rank's frames needed a larger canvas: form this GOF again on it
                         stats["reformed"] += 1
-                        _, _, nbytes = phase_b(gof, Wg, Hg)
+                        _, _, nbytes = phase_b(lane, gof, Wg, Hg)
                 spans = prods[lane].profile_read()
                 gof.free()
                 tf = time.perf_counter()
                 host_phases.append((ta - t0, t1 - ta, t2 - t1, (tv - t2) + tw, tf - t0))
                 gof_log.append((lane, t0, ta, t1, t2, tv, tf))
-                results[g] = (t1 - t0, t2 - t0, spans, nbytes)
+                results[g] = (t1 - t0, t2 - t0, spans, nbytes, lane)
 
         in_threads(worker, min(lanes, count))
         xs = None
@@ -458,7 +458,7 @@ def main():
     ires, _ = run_steps(lanes)
     wres, _ = run_steps(args.warmup) if args.warmup > 0 else ([], None)
     if lanes > 1:   # steady-state spacing of GOF starts: latency of one (warm) GOF / lanes
-        stagger[0] = float(np.min([e for _, e, _, _ in (wres or ires)])) / lanes
+        stagger[0] = float(np.min([r[1] for r in (wres or ires)])) / lanes
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -477,11 +477,11 @@ def main():
     # device window per GOF (first compute span to last span of any of its frame streams); GOFs overlap, so the job's device time
     # is bounded by the wall clock of the timed region: report the smaller of the two views consistently as wall-based
     dev_each = []
-    for c, e, spans, nb in res:
+    for c, e, spans, nb, _ in res:
         comp = [(st, st + ms) for nme, ms, st in spans if st >= 0 and nme not in ("h2d", "d2h_patches")]
         dev_each.append((max(b for a, b in comp) - min(a for a, b in comp)) / 1e3 if comp else c)
     e2e_t = wall_total
-    dev_t = wall_total - (sum(e - c for c, e, _, _ in res) / max(1, lanes))   # wall minus the hand-off copies of one lane
+    dev_t = wall_total - (sum(r[1] - r[0] for r in res) / max(1, lanes))   # wall minus the hand-off copies of one lane
     if lanes == 1:
         dev_t = float(np.sum(dev_each))
     if dist is not None:
@@ -553,7 +553,8 @@ def main():
             out["roofline"]["traffic"] = int(lc["traffic_bytes_per_frame"][dom] * per_launch[dom])
             out["roofline"]["traffic_source"] = lc.get("traffic_source")
     if not args.no_cpu_baseline:
-        last = {what: outbuf[(0, what)] for what in HANDOFF if (0, what) in outbuf} if args.frames > 0 else None
+        last_lane = res[-1][4]
+        last = {what: outbuf[(last_lane, 0, what)] for what in HANDOFF if (last_lane, 0, what) in outbuf} if args.frames > 0 else None
         sec, info = parity_check(prod, frames[0], prm, prec, last)
         out.update(info)
         if sec is not None:
