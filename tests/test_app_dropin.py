@@ -145,6 +145,22 @@ def decoder_command(binary, work, stream, out):
            ["--videoDecoder%sPath=%s" % (k, STUB) for k in ("Occupancy", "Geometry", "Attribute")]
 
 
+@pytest.mark.skipif(not have_apps(), reason="oracle/_ref/bin not built (needs /root/reference at build time)")
+def test_reference_applications_round_trip_through_the_codec_stub(tmp_path):
+    """CPU: pins the test infrastructure itself - with the pass-through stub (incl. its hand-made HEVC SPS, which the reference's
+    parser must read the frame sizes from) the UNMODIFIED decoder reproduces the unmodified encoder's reconstruction and passes its
+    own checksum comparison"""
+    work = str(tmp_path)
+    make_inputs(work, 2, 0.1)
+    assert run(encoder_command("PccAppEncoder", work, os.path.join(work, "enc"), "ai_r3", 2, 2), os.path.join(work, "enc.log")) == 0
+    assert run(decoder_command("PccAppDecoder", work, os.path.join(work, "enc", "s.bin"), os.path.join(work, "dec")), os.path.join(work, "dec.log")) == 0
+    enc, dec = digest_dir(os.path.join(work, "enc")), digest_dir(os.path.join(work, "dec"))
+    assert [dec["dec_%04d.ply" % f] for f in range(2)] == [enc["rec_%04d.ply" % f] for f in range(2)]
+    with open(os.path.join(work, "dec.log")) as f:
+        log = f.read()
+    assert "hevcParser= 1280 x 1280 8 bits" in log and "hevcParser= 320 x 320 8 bits" in log
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not have_apps(), reason="oracle/_ref/bin not built (needs /root/reference at build time)")
 def test_b200_decoder_application_reconstructs_what_the_reference_decoder_does(tmp_path):
