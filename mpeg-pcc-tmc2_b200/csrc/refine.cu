@@ -542,9 +542,11 @@ void refineSegmentation( RefineScratch& sc, const short4* pts, const double* nor
     const char* e = getenv( "PCCB200_SWEEP_CTAS_PER_SM" );
     return e && atoi( e ) > 0 ? atoi( e ) : 8;
   }();
-  static const int tailCtasPerSm = [] {  // (the tail of a sweep is about as long as its initial list: same order of warps)
+  // (tuning knob of the tail: its warps mostly WAIT - for tickets, for cascades - so few of them is better when other frames' kernels
+  //  share the SMs: 2 / 4 / 8 CTAs per SM gave 56.1 / 52.5 / 48.5 Mpoints/s in the default bench, profiles/r02f, r02h, r02k)
+  static const int tailCtasPerSm = [] {
     const char* e = getenv( "PCCB200_SWEEP_TAIL_CTAS_PER_SM" );
-    return e && atoi( e ) > 0 ? atoi( e ) : 4;
+    return e && atoi( e ) > 0 ? atoi( e ) : 2;
   }();
   const int staticCtas = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * ctasPerSm ) );
   const int tailCtas   = int( std::min<size_t>( divUp( V, 4 ), size_t( 148 ) * tailCtasPerSm ) );
