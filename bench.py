@@ -6,7 +6,7 @@
 
 Workloads (BASELINE.json configs): default = configs[1] (longdress-like, 10 bit, 0.83 Mpts/frame, CTC all-intra r3, I=50);
 `--condition ra` = configs[2] (random-access r5: occupancyPrecision 2, global patch allocation); `--bits 11` = configs[4]
-(~2.9 Mpts/frame, 2560-wide canvas, I=20; use --frames 8 --gofs-in-flight 3: a frame keeps ~1.6 GB while in flight);
+(~2.9 Mpts/frame, 2560-wide canvas, I=20; use --frames 8 --gofs-in-flight 8 --scratch-sets 8: a frame keeps ~1.6 GB while in flight);
 `--ply-dir DIR` replaces the synthetic figure by real frames (e.g. longdress_vox10_1051..1082.ply) read by pccb200_ply_read.
 
 One "step" = one GOF (--frames F frames per GPU) of synthetic longdress-like frames (tests/synth.py `figure`, 10-bit, ≈0.83 M points
@@ -23,12 +23,15 @@ Multi-GPU (torchrun, one process per GPU): the frames of every GOF are sharded o
 an N*F-frame GOF: weak scaling); the one cross-frame coupling of the all-intra path — the common canvas size — is an
 NCCL all-reduce(MAX) issued by a comm thread on its own communicator / high-priority stream, several GOFs per collective, and
 taken off the critical path: image formation goes ahead on the local size and the reduced size is checked before the GOF is
-handed off (mpeg-pcc-tmc2_b200/sharding.py).  Timing: barrier + synchronize on both sides, max over ranks.
+handed off (mpeg-pcc-tmc2_b200/sharding.py). Random access (--condition ra) shards the same way; every frame is packed against the
+previous one there, so the ranks all-gather the patch records (KBs of host data per frame: a gloo group) once per GOF and every rank
+runs the deterministic packing (pccb200_gof_pack_ra).  Timing: barrier + synchronize on both sides, max over ranks.
 
 JSON keys follow the driver contract.  value = throughput over the DEVICE window (first compute span to last span of any
 frame stream, CUDA events; input already uploaded), e2e = wall clock through the C ABI with host buffers including the
-H2D of the clouds and the D2H of every frame handed to the video codec, roofline = dominant kernel, cpu_baseline = the
-reference's own CPU code (oracle/_ref) on a bounded sample.
+H2D of the clouds and the D2H of every frame handed to the video codec (per-lane pinned buffers), roofline = the stage span with the
+longest duration plus a per-stage table and the whole-path figure, cpu_baseline = the reference's own CPU code (oracle/_ref) on a
+bounded sample (one frame), against whose products frame 0 of this run is compared ("parity_checked" / "parity_ok").
 """
 import argparse
 import json

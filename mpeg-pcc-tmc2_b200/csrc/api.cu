@@ -32,7 +32,12 @@ int pccb200_create( int device, pccb200_ctx** out ) {
   pccb200_ctx* c = new ( std::nothrow ) pccb200_ctx();
   if ( !c ) return PCCB200_ERR_CUDA;
   c->device = device;
-  if ( cudaSetDevice( device ) != cudaSuccess || cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) != cudaSuccess ) {
+  // The context's own stream carries the GOF-level work that is latency-critical and tiny: the batched orientation walks (one warp
+  // per frame) and the single-CTA placement searches of the random-access packer, which the host waits for launch by launch. It gets
+  // the highest priority, so that these CTAs take the next free SM slot instead of queueing behind the frames' N-sized grids.
+  int prioLow = 0, prioHigh = 0;
+  if ( cudaSetDevice( device ) == cudaSuccess ) cudaDeviceGetStreamPriorityRange( &prioLow, &prioHigh );
+  if ( cudaSetDevice( device ) != cudaSuccess || cudaStreamCreateWithPriority( &c->stream, cudaStreamNonBlocking, prioHigh ) != cudaSuccess ) {
     cudaGetLastError();
     delete c;
     return PCCB200_ERR_CUDA;
