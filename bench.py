@@ -48,7 +48,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 METRIC = "Mpoints/s patch-gen+image-formation, longdress_vox10, 1/2/4/8 GPU"
-HANDOFF = (2, 4, 5, 15, 16)  # what the video codec receives: OM video, geometry D0/D1 luma, padded attribute T0/T1 as 8-bit YUV 4:2:0
+HANDOFF = (2, 17, 18, 15, 16)  # what the video codec receives: OM video, geometry D0/D1 luma as bytes, padded attribute T0/T1 as 8-bit YUV 4:2:0
 
 
 def pinned(shape, dtype):
@@ -193,7 +193,7 @@ def config(args, npts, frames_per_rank, world):
                            "frames of a GOF sharded over %d GPU(s) (frame f -> GPU f mod G), one all-gather of the patch records (host data, gloo) per GOF, packing replicated" % world,
             "l2": "per-frame working set (>400 MB) and fresh uploads every step exceed the 126 MB L2",
             "host_buffers": "pinned (inputs and the frames handed to the video codec)",
-            "handoff": "occupancy video + geometry D0/D1 luma + attribute T0/T1 converted to 8-bit YUV 4:2:0 on the device (the conversion the reference does inside compress())",
+            "handoff": "occupancy video + geometry D0/D1 luma as bytes + attribute T0/T1 converted to 8-bit YUV 4:2:0 on the device (the conversion the reference does inside compress())",
             "scratch_sets": args.scratch_sets}
 
 
@@ -270,7 +270,9 @@ def parity_check(prod, frame0, prm, prec, handoff_of_last_gof):
                 info = {"parity_checked": True, "parity_ok": bad == [], "parity_against": "tests/golden/gof_fullsize.json (sha256 of the reference's products, frame 0)", "parity_mismatches": bad[:6]}
     # the frames the TIMED pipeline handed off are the ones just checked (same frame, same canvas)
     if handoff_of_last_gof is not None and info.get("parity_checked"):
-        same = all(np.array_equal(buf, got[0].data[what]) for what, buf in handoff_of_last_gof.items() if buf.size == got[0].data[what].size)
+        def checked(what):   # the byte forms of the geometry planes are GEO0 / GEO1 of the checked frame, narrowed
+            return got[0].data[what - 13].astype(np.uint8) if what in (17, 18) else got[0].data[what]
+        same = all(np.array_equal(buf, checked(what)) for what, buf in handoff_of_last_gof.items() if buf.size == checked(what).size)
         info["timed_handoff_matches_checked_frame"] = bool(same)
     return sec, info
 
@@ -371,7 +373,7 @@ def main():
                 cnt = g.count(f, what)
                 key = (lane, f, what)
                 if key not in outbuf or outbuf[key].size != cnt:
-                    outbuf[key] = pinned((cnt,), bindings.GOF_DTYPES[what])
+                    outbuf[key] = pinned((cnt,), bindings.GOF_DTYPES.get(what) or bindings.GOF_EXTRA_DTYPES[what])
                 g.fetch(f, what, outbuf[key])
                 nbytes += outbuf[key].nbytes
         return t1, time.perf_counter(), nbytes

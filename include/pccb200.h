@@ -226,7 +226,12 @@ enum {
    * 326-353): RGB444 -> YUV 4:2:0, 8 bit, PCCInternalColorConverter "RGB444ToYUV420_8_4" (the default down-sampling filter).
    * Planes Y (W*H), U, V ((W/2)*(H/2) each); converted on the device when requested: a quarter of the bytes of ATTR0/ATTR1. */
   PCCB200_GOF_ATTR0_YUV420   = 15, /* uint8  W*H*3/2 */
-  PCCB200_GOF_ATTR1_YUV420   = 16  /* uint8  W*H*3/2 */
+  PCCB200_GOF_ATTR1_YUV420   = 16, /* uint8  W*H*3/2 */
+  /* the geometry luma planes as the 8-bit codec input holds them (PCCVideo::write with one byte per sample,
+   * PccLibCommon/include/PCCImage.h / PCCVideo.h; geometryNominal2dBitdepth 8): the values of GEO0 / GEO1 narrowed on the device, half the
+   * bytes over PCIe. The chroma planes of the 4:2:0 file are constant (the geometry frames carry luma only). */
+  PCCB200_GOF_GEO0_LUMA8     = 17, /* uint8  W*H */
+  PCCB200_GOF_GEO1_LUMA8     = 18  /* uint8  W*H */
 };
 size_t pccb200_gof_get( pccb200_gof* gof, int f, int what, void* dst );
 

@@ -34,6 +34,7 @@ struct FrameState {
   ReconScratch               rc;
   AttrImages                 attr;
   YuvScratch                 yuv;
+  DevBuf<uint8_t>            geoLuma8;  // GEO0 / GEO1 narrowed to bytes on request (hand-off to an 8-bit codec)
   Profiler                   prof;
   bool                       decodedSet = false;  // the caller replaced om/geo0/geo1 by decoded planes
   int                        status = 0;

@@ -316,6 +316,10 @@ __global__ void kUnpackXyz( const short4* __restrict__ in, int n, int16_t* __res
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if ( i < n ) out[3 * size_t( i )] = in[i].x, out[3 * size_t( i ) + 1] = in[i].y, out[3 * size_t( i ) + 2] = in[i].z;
 }
+__global__ void kNarrowU16( const uint16_t* __restrict__ in, size_t n, uint8_t* __restrict__ out ) {
+  const size_t i = size_t( blockIdx.x ) * blockDim.x + threadIdx.x;
+  if ( i < n ) out[i] = uint8_t( in[i] );  // (what PCCImage::write does for one byte per sample: a plain narrowing cast)
+}
 __global__ void kUnpackRgb( const uchar4* __restrict__ in, int n, uint8_t* __restrict__ out ) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if ( i < n ) out[3 * size_t( i )] = in[i].x, out[3 * size_t( i ) + 1] = in[i].y, out[3 * size_t( i ) + 2] = in[i].z;
@@ -687,9 +691,9 @@ size_t pccb200_gof_get( pccb200_gof* g, int f, int what, void* dst ) {
   guarded( g->ctx, [&]() -> int {
     const size_t Q = g->W * g->H, cells = ( g->W / g->occPrec ) * ( g->H / g->occPrec ), blocks = ( g->W / 16 ) * ( g->H / 16 );
     const size_t R = g->stage >= 3 ? fs.rc.numPoints : 0;
-    if ( what >= 1 && what <= 5 && g->stage < 2 ) return 0;
+    if ( ( ( what >= 1 && what <= 5 ) || what == PCCB200_GOF_GEO0_LUMA8 || what == PCCB200_GOF_GEO1_LUMA8 ) && g->stage < 2 ) return 0;
     if ( what >= 6 && what <= 9 && g->stage < 3 ) return 0;
-    if ( what >= 10 && g->stage < 4 ) return 0;
+    if ( what >= 10 && what <= 16 && g->stage < 4 ) return 0;
     switch ( what ) {
       case PCCB200_GOF_OCCUPANCY: result = copyOut( dst, fs.im.occ, Q, 1, s ); break;
       case PCCB200_GOF_OM_VIDEO: result = copyOut( dst, fs.im.om, cells, 1, s ); break;
@@ -719,6 +723,15 @@ size_t pccb200_gof_get( pccb200_gof* g, int f, int what, void* dst ) {
       case PCCB200_GOF_ATTR1_RAW: result = copyOut( dst, fs.attr.rawPlanes[1], 3 * Q, 2, s ); break;
       case PCCB200_GOF_ATTR0: result = copyOut( dst, fs.attr.planes[0], 3 * Q, 2, s ); break;
       case PCCB200_GOF_ATTR1: result = copyOut( dst, fs.attr.planes[1], 3 * Q, 2, s ); break;
+      case PCCB200_GOF_GEO0_LUMA8:
+      case PCCB200_GOF_GEO1_LUMA8:
+        result = Q;
+        if ( dst ) {
+          fs.geoLuma8.reserve( Q );
+          kNarrowU16<<<divUp( Q, 256 ), 256, 0, s>>>( what == PCCB200_GOF_GEO0_LUMA8 ? fs.im.geo0.p : fs.im.geo1.p, Q, fs.geoLuma8 );
+          copyOut( dst, fs.geoLuma8, Q, 1, s );
+        }
+        break;
       case PCCB200_GOF_ATTR0_YUV420:
       case PCCB200_GOF_ATTR1_YUV420: {
         const int m = what == PCCB200_GOF_ATTR0_YUV420 ? 0 : 1;

@@ -417,6 +417,8 @@ class Product:
 GOF_OCCUPANCY, GOF_OM_VIDEO, GOF_BLOCK_TO_PATCH, GOF_GEO0, GOF_GEO1, GOF_REC_XYZ, GOF_POINT_TO_PIXEL = 1, 2, 3, 4, 5, 6, 7
 GOF_REC_PARTITION, GOF_REC_BOUNDARY, GOF_REC_RGB, GOF_ATTR0_RAW, GOF_ATTR1_RAW, GOF_ATTR0, GOF_ATTR1 = 8, 9, 10, 11, 12, 13, 14
 GOF_ATTR0_YUV420, GOF_ATTR1_YUV420 = 15, 16
+GOF_GEO0_LUMA8, GOF_GEO1_LUMA8 = 17, 18   # product-only hand-off forms (not produced by the oracle / reference harness: == GEO0 / GEO1 as bytes)
+GOF_EXTRA_DTYPES = {17: np.uint8, 18: np.uint8}
 GOF_DTYPES = {1: np.uint8, 2: np.uint8, 3: np.uint32, 4: np.uint16, 5: np.uint16, 6: np.int16, 7: np.uint32, 8: np.uint32,
               9: np.uint16, 10: np.uint8, 11: np.uint16, 12: np.uint16, 13: np.uint16, 14: np.uint16, 15: np.uint8, 16: np.uint8}
 
@@ -693,7 +695,7 @@ class ProductGof:
     def fetch(self, f, what, out=None):
         cnt = self.p.lib.pccb200_gof_get(self.h, f, what, None)
         if out is None or out.size != cnt:
-            out = np.empty(cnt, GOF_DTYPES[what])
+            out = np.empty(cnt, GOF_DTYPES.get(what) or GOF_EXTRA_DTYPES[what])
         if cnt:
             self.p.lib.pccb200_gof_get(self.h, f, what, out.ctypes.data_as(C.c_void_p))
         return out

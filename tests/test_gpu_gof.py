@@ -156,3 +156,17 @@ def test_decoder_rejects_patches_outside_the_canvas(oracle, product):
             product.generate_point_cloud(bad, *args)
     with pytest.raises(RuntimeError):
         product.generate_point_cloud(fr.patches.patches, fr[bindings.GOF_OM_VIDEO], fr[bindings.GOF_GEO0], fr[bindings.GOF_GEO1], 0, fr.height)
+
+
+def test_geometry_luma_as_bytes(product):
+    """PCCB200_GOF_GEO0_LUMA8 / GEO1_LUMA8: the geometry planes narrowed on the device for an 8-bit codec (half the D2H bytes)"""
+    frames = [synth.figure(scale=0.2, seed=6, frame=0)]
+    prm = ctc_seg_params(bits=10, iterations=4, weight=product.weight_normal(frames[0][0], 11))
+    g = bindings.ProductGof(product, frames, prm, 4)
+    assert g.count(0, bindings.GOF_GEO0_LUMA8) == 0          # not before the geometry images exist
+    W, H, _ = g.dims(0)
+    g.resume(W, H, 2)
+    for wide, narrow in ((bindings.GOF_GEO0, bindings.GOF_GEO0_LUMA8), (bindings.GOF_GEO1, bindings.GOF_GEO1_LUMA8)):
+        a, b = g.fetch(0, wide), g.fetch(0, narrow)
+        assert b.dtype == np.uint8 and b.size == W * H and int(a.max()) <= 255 and np.array_equal(a.astype(np.uint8), b)
+    g.free()
