@@ -102,6 +102,16 @@ int         pccb200_set_scratch_sets( int device, int count );
  * (pin them: they are what pccb200_encode_gof uploads). Host code, no device needed. Call with xyz == NULL to get the point
  * count of the header in *n; capacity is in points; *has_colours (may be NULL) tells whether rgb was filled. */
 int pccb200_ply_read( const char* path, int16_t* xyz, uint8_t* rgb, size_t capacity, size_t* n, int* has_colours );
+/* PCCGroupOfFrames::load (PccLibCommon/source/PCCGroupOfFrames.cpp:46-83) on top of it: frame k (0 <= k < end_frame -
+ * start_frame) is the file sprintf( path_pattern, start_frame + k ) - the pattern of --uncompressedDataPath, e.g.
+ * "longdress_vox10_%04d.ply". xyz / rgb / capacity / n / has_colours are arrays with one entry per frame; xyz == NULL asks for
+ * the point counts (n) and colour flags only. The frames are read by `threads` host threads (<= 0: all cores), several frames
+ * at a time. Like the reference, the group ends at the first frame that cannot be read: *frames_read (may be NULL) receives
+ * the number of good frames in front of it and the status of that frame is returned (PCCB200_OK when all were read; the
+ * buffers of later frames may have been written). end_frame == start_frame is an empty group (OK, nothing read; the
+ * reference's load returns false for it). Host code, no device needed. */
+int pccb200_ply_read_frames( const char* path_pattern, size_t start_frame, size_t end_frame, int16_t* const* xyz, uint8_t* const* rgb,
+                             const size_t* capacity, size_t* n, int* has_colours, int threads, size_t* frames_read );
 
 /* Per-stage device timing (CUDA events on the launching stream). While enabled, every entry point appends one
  * (name, milliseconds) record per stage and frame; read returns and clears them. names: capacity x 32 chars; start_ms

@@ -333,4 +333,48 @@ int yuv16ToRgb8( Session& s, PCCPointSet3& cloud ) {
   return pccb200_yuv16_to_rgb8( s.ctx, &cloud.getColors16bit()[0][0], n, &cloud.getColors()[0][0] );
 }
 
+bool loadFrames( PCCGroupOfFrames& frames, const std::string& path, size_t startFrameNumber, size_t endFrameNumber,
+                 PCCColorTransform colorTransform, size_t nbThread ) {
+  static_assert( sizeof( PCCPoint3D ) == 3 * sizeof( int16_t ) && sizeof( PCCColor3B ) == 3, "point sets are read in place" );
+  if ( endFrameNumber < startFrameNumber ) return false;
+  const size_t count = endFrameNumber - startFrameNumber;
+  frames.setFrameCount( count );
+  if ( count == 0 ) return false;
+  // pass 1, headers: point counts and colour flags; the group ends in front of the first unreadable file
+  std::vector<size_t> n( count, 0 );
+  std::vector<int>    colours( count, 0 );
+  size_t              good = 0;
+  pccb200_ply_read_frames( path.c_str(), startFrameNumber, endFrameNumber, nullptr, nullptr, nullptr, n.data(), colours.data(), int( nbThread ), &good );
+  std::vector<int16_t*> xyz( count, nullptr );
+  std::vector<uint8_t*> rgb( count, nullptr );
+  for ( size_t k = 0; k < good; ++k ) {
+    auto& ps = frames[k];
+    ps.resize( 0 );
+    ps.removeNormals();
+    ps.removeReflectances();
+    if ( colours[k] ) ps.addColors();
+    else ps.removeColors();
+    ps.resize( n[k] );
+    xyz[k] = n[k] ? &ps.getPositions()[0][0] : nullptr;
+    rgb[k] = ( n[k] && colours[k] ) ? &ps.getColors()[0][0] : nullptr;
+  }
+  // pass 2, bodies (a frame without points has nothing to parse: its buffers stay null, which asks for its header again)
+  if ( good ) {
+    std::vector<size_t> capacity( n );
+    size_t              read = 0;
+    pccb200_ply_read_frames( path.c_str(), startFrameNumber, startFrameNumber + good, xyz.data(), rgb.data(), capacity.data(), n.data(), nullptr,
+                             int( nbThread ), &read );
+    good = read;  // (smaller after a body line with too few values: the reference's read() fails there as well)
+  }
+  if ( good < count ) {
+    char fileName[4096];
+    snprintf( fileName, sizeof( fileName ), path.c_str(), startFrameNumber + good );
+    printf( "Error: can't open %s\n", fileName );
+    frames.setFrameCount( good );
+  }
+  if ( colorTransform == COLOR_TRANSFORM_RGB_TO_YCBCR )
+    for ( size_t k = 0; k < good; ++k ) frames[k].convertRGBToYUV();
+  return true;
+}
+
 }  // namespace pccb200shim

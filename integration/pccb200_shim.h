@@ -57,4 +57,12 @@ int smoothGeometry( Session& s, pcc::PCCPointSet3& reconstruct, const std::vecto
 int transferColors16( Session& s, pcc::PCCPointSet3& source, pcc::PCCPointSet3& target );
 int yuv16ToRgb8( Session& s, pcc::PCCPointSet3& cloud );
 
+// Input side: drop-in body for PCCGroupOfFrames::load( path, start, end, colorTransform, false, nbThread )
+// (PccLibCommon/source/PCCGroupOfFrames.cpp:46-83; the call of PccAppEncoder.cpp:1048) - positions and colours of every frame,
+// parsed by pccb200_ply_read_frames straight into the point sets' own storage, several frames at a time. Same result and return
+// value as the reference's: the group is cut at the first frame that cannot be read, false only for an empty range. Normals and
+// reflectances, which the encoder does not read from its sources, are not loaded. Host code, no device needed.
+bool loadFrames( pcc::PCCGroupOfFrames& frames, const std::string& path, size_t startFrameNumber, size_t endFrameNumber,
+                 pcc::PCCColorTransform colorTransform, size_t nbThread );
+
 }  // namespace pccb200shim

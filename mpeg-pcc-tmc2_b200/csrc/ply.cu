@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -175,7 +176,8 @@ bool forLines( const char* data, const Chunk& c, size_t maxTokens, F&& emit ) {
 
 }  // namespace
 
-extern "C" int pccb200_ply_read( const char* path, int16_t* xyz, uint8_t* rgb, size_t capacity, size_t* n, int* hasColours ) {
+// one frame; an ascii body is parsed by up to maxThreads threads
+static int readOne( const char* path, int16_t* xyz, uint8_t* rgb, size_t capacity, size_t* n, int* hasColours, size_t maxThreads ) {
   if ( !path || !n ) return PCCB200_ERR_BAD_ARG;
   *n = 0;
   FILE* f = fopen( path, "rb" );
@@ -183,12 +185,19 @@ extern "C" int pccb200_ply_read( const char* path, int16_t* xyz, uint8_t* rgb, s
   fseek( f, 0, SEEK_END );
   const long fileSize = ftell( f );
   fseek( f, 0, SEEK_SET );
-  std::vector<char> file( fileSize > 0 ? size_t( fileSize ) : 0 );
-  const size_t      got = file.empty() ? 0 : fread( file.data(), 1, file.size(), f );
+  // (a size query needs the header only: the first 64 KB, the whole file if the header should be longer than that)
+  const size_t      whole = fileSize > 0 ? size_t( fileSize ) : 0;
+  std::vector<char> file( xyz ? whole : std::min<size_t>( whole, 65536 ) );
+  size_t            got = file.empty() ? 0 : fread( file.data(), 1, file.size(), f );
+  Header            h;
+  int               rc = got == file.size() ? parseHeader( file.data(), file.size(), h ) : PCCB200_ERR_BAD_ARG;
+  if ( rc != PCCB200_OK && got == file.size() && file.size() < whole ) {
+    file.resize( whole );
+    got += fread( file.data() + got, 1, whole - got, f );
+    h  = Header();
+    rc = got == whole ? parseHeader( file.data(), file.size(), h ) : PCCB200_ERR_BAD_ARG;
+  }
   fclose( f );
-  if ( got != file.size() ) return PCCB200_ERR_BAD_ARG;
-  Header    h;
-  const int rc = parseHeader( file.data(), file.size(), h );
   if ( rc != PCCB200_OK ) return rc;
   if ( hasColours ) *hasColours = h.colours ? 1 : 0;
   *n = h.count;
@@ -200,7 +209,7 @@ extern "C" int pccb200_ply_read( const char* path, int16_t* xyz, uint8_t* rgb, s
   if ( rgb && h.colours ) memset( rgb, 0, h.count * 3 );
   if ( h.ascii ) {
     const size_t body    = size - h.bodyOffset;
-    const int    threads = int( std::max<size_t>( 1, std::min<size_t>( std::min<size_t>( 8, std::thread::hardware_concurrency() ), body >> 20 ) ) );
+    const int    threads = int( std::max<size_t>( 1, std::min<size_t>( std::min<size_t>( maxThreads, std::thread::hardware_concurrency() ), body >> 20 ) ) );
     std::vector<Chunk> chunks( threads );
     size_t             at = h.bodyOffset;
     for ( int t = 0; t < threads; ++t ) {
@@ -284,4 +293,45 @@ extern "C" int pccb200_ply_read( const char* path, int16_t* xyz, uint8_t* rgb, s
     }
   }
   return PCCB200_OK;
+}
+
+extern "C" int pccb200_ply_read( const char* path, int16_t* xyz, uint8_t* rgb, size_t capacity, size_t* n, int* hasColours ) {
+  return readOne( path, xyz, rgb, capacity, n, hasColours, 8 );
+}
+
+// PCCGroupOfFrames::load (PccLibCommon/source/PCCGroupOfFrames.cpp:46-83): frame k of the group is the file sprintf( pattern,
+// start + k ); the reference reads them one after the other (in parallel only in a TBB build) and cuts the group at the first
+// file it cannot read. Here `threads` workers take the frames in order and share the remaining threads for the ascii bodies.
+extern "C" int pccb200_ply_read_frames( const char* pathPattern, size_t startFrame, size_t endFrame, int16_t* const* xyz, uint8_t* const* rgb,
+                                        const size_t* capacity, size_t* n, int* hasColours, int threads, size_t* framesRead ) {
+  if ( framesRead ) *framesRead = 0;
+  if ( !pathPattern || !n || endFrame < startFrame || ( xyz && !capacity ) ) return PCCB200_ERR_BAD_ARG;
+  const size_t count = endFrame - startFrame;
+  if ( count == 0 ) return PCCB200_OK;
+  size_t hw = std::thread::hardware_concurrency();
+  if ( hw == 0 ) hw = 1;
+  const size_t total   = threads > 0 ? size_t( threads ) : hw;
+  const size_t workers = std::max<size_t>( 1, std::min( total, count ) );
+  const size_t inner   = std::max<size_t>( 1, std::min<size_t>( 8, total / workers ) );
+  std::vector<int>    status( count, PCCB200_OK );
+  std::atomic<size_t> next( 0 );
+  auto work = [&]() {
+    for ( ;; ) {
+      const size_t k = next.fetch_add( 1 );
+      if ( k >= count ) return;
+      char name[4096];
+      snprintf( name, sizeof( name ), pathPattern, startFrame + k );  // (a size_t behind the caller's %d pattern, as in the reference)
+      int colours = 0;
+      status[k]   = readOne( name, xyz ? xyz[k] : nullptr, ( xyz && rgb ) ? rgb[k] : nullptr, xyz ? capacity[k] : 0, &n[k], &colours, inner );
+      if ( hasColours ) hasColours[k] = colours;
+    }
+  };
+  std::vector<std::thread> pool;
+  for ( size_t t = 1; t < workers; ++t ) pool.emplace_back( work );
+  work();
+  for ( auto& t : pool ) t.join();
+  size_t good = 0;
+  while ( good < count && status[good] == PCCB200_OK ) ++good;
+  if ( framesRead ) *framesRead = good;
+  return good == count ? PCCB200_OK : status[good];
 }
